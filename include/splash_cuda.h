@@ -1,0 +1,186 @@
+/*
+ * splash_cuda.h -- C ABI of libsplash_cuda, the B200 drop-in for the splash.grid()/splash.point()
+ * hot path of dsval/rsplash (SPLASH v2.0).
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   splash_grid_run   <- the per-block worker body `clFun`: mapply(splash.point, sw_in=, tc=, pn=,
+ *                        lat=, elev=, slop=, asp=, soil_data=, Au=, resolution=, MoreArgs=...)
+ *                        R/splash.grid.R:277-308, and for every cell the three Rcpp-module calls it
+ *                        makes, R/splash.point.R:92 (new(SPLASH,lat,elev)), :148/:152
+ *                        ($spin_up, src/SPLASH.cpp:1594-1749) and :158-172 ($run_all,
+ *                        src/SPLASH.cpp:1833-1916), plus the per-cell R arithmetic around them
+ *                        (R/splash.point.R:96-131 soil_hydro / snow partition, :147-150 aridity
+ *                        quirk, :182-214 sm_lim and monthly aggregation).
+ *   splash_point_run  <- splash.point() itself, R/splash.point.R:29-225 (one cell).
+ *   splash_ctx_create / _destroy <- raster::beginCluster / endCluster, R/splash.grid.R:32-39
+ *                        (the PSOCK worker pool is what the GPU context stands in for).
+ *   splash_last_error <- the only error path of the reference scheduler,
+ *                        `stop('cluster error:')`, R/splash.grid.R:363-365.
+ *
+ * Layout contract: forcing matrices are DAY-MAJOR with cells contiguous, element (day d, cell c) at
+ * [d * cell_stride + c].  This is exactly what raster::getValues(brick, row, nrows) hands to R
+ * (column-major [cells x layers], R/splash.grid.R:278-280), so the R glue passes REAL() pointers
+ * through unchanged.  Outputs use the same layout with n_out layers (= n_days, or the number of
+ * calendar months when monthly_out is set), matching do.call(rbind, value[k,]) at
+ * R/splash.grid.R:370-378.
+ *
+ * Ownership: the caller owns every buffer it passes in (inputs and outputs); the library keeps no
+ * pointer after a call returns.  Device buffers, pinned staging memory and streams live in the
+ * context.  A context is bound to one CUDA device and is not re-entrant: one call at a time.
+ * There is no CPU fallback: without a usable CUDA device splash_ctx_create fails.
+ *
+ * NaN inputs are data, not errors: they propagate exactly as in the reference (per-layer NA masks).
+ */
+#ifndef SPLASH_CUDA_H
+#define SPLASH_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPLASH_ABI_VERSION 1
+
+/* status codes */
+enum {
+    SPLASH_OK = 0,
+    SPLASH_ERR_BAD_ARG = 1,  /* NULL/negative/inconsistent argument */
+    SPLASH_ERR_CUDA = 2,     /* a CUDA runtime call failed (see splash_last_error) */
+    SPLASH_ERR_NOMEM = 3,    /* device or pinned-host allocation failed */
+    SPLASH_ERR_NO_DEVICE = 4 /* no usable sm_100 device: there is no CPU fallback */
+};
+
+/* where the caller's pointers live */
+enum { SPLASH_MEM_HOST = 0, SPLASH_MEM_DEVICE = 1 };
+/* element type of the three forcing matrices (everything else is always f64) */
+enum { SPLASH_F64 = 0, SPLASH_F32 = 1 };
+
+/* layers of splash_grid_out.cell_diag, [SPLASH_NDIAG * n_cells], layer-major */
+enum {
+    SPLASH_DIAG_SAT = 0,   /* soil_info[0]  saturation, mm            R/splash.point.R:98  */
+    SPLASH_DIAG_WP = 1,    /* soil_info[1]  wilting point, mm         :99  */
+    SPLASH_DIAG_FC = 2,    /* soil_info[2]  field capacity, mm        :100 */
+    SPLASH_DIAG_KSAT = 3,  /* soil_info[3]  mm/h                      :355-363 */
+    SPLASH_DIAG_LAMBDA = 4,/* soil_info[4]  1/B                       :104 */
+    SPLASH_DIAG_DEPTH = 5, /* soil_info[5]  m                         :97  */
+    SPLASH_DIAG_BUB = 6,   /* soil_info[6]  air-entry pressure, mm    :369-380 */
+    SPLASH_DIAG_RES = 7,   /* soil_info[7]  residual, mm              :101 */
+    SPLASH_DIAG_WMAX_R = 8,/* theta_c*depth*1000 used by sm_lim       :102,197 */
+    SPLASH_DIAG_TT = 9,    /* snowfall threshold temperature Tt       :122 */
+    SPLASH_DIAG_AI = 10,   /* sum(pet)/sum(P) of the first spin-up    :150 */
+    SPLASH_DIAG_SPIN_PASSES = 11, /* year passes executed by the 2nd spin_up (1..1000) */
+    SPLASH_DIAG_SNOW_DAYS = 12,   /* number of days with p_snow >= 0.5 (occurrence flags) */
+    SPLASH_DIAG_SNOWFALL_DAYS = 13, /* number of days with snowfall > 0 */
+    SPLASH_NDIAG = 14
+};
+
+typedef struct splash_ctx splash_ctx;
+
+/* Inputs of one block of cells == the mapply() argument set of R/splash.grid.R:291-304. */
+typedef struct splash_grid_in {
+    int64_t n_cells;        /* cells in this block */
+    int64_t n_days;         /* length of the daily series */
+    int64_t cell_stride;    /* elements between consecutive days in sw_in/tc/pn; 0 means n_cells */
+    const int32_t* year;    /* [n_days] calendar year of each day   (format(time_index,'%Y'), splash.point.R:59) */
+    const int32_t* doy;     /* [n_days] day of year 1..366          (format(time_index,'%j'), :57) */
+    const int32_t* month;   /* [n_days] month 1..12                 (format(time_index,'%m'), :547) */
+    const void* sw_in;      /* [n_days*cell_stride] shortwave radiation, W m-2 */
+    const void* tc;         /* [n_days*cell_stride] air temperature, deg C */
+    const void* pn;         /* [n_days*cell_stride] precipitation, mm day-1 */
+    const double* lat;      /* [n_cells] latitude, deg */
+    const double* elev;     /* [n_cells] elevation, m */
+    const double* slop;     /* [n_cells] slope, deg */
+    const double* asp;      /* [n_cells] aspect, deg clockwise from north (library applies asp-180, splash.point.R:131) */
+    const double* resolution; /* [n_cells] cell size, m */
+    const double* soil;     /* [6*n_cells] layer-major: sand %, clay %, OM %, gravel %, bulk density g cm-3 (NaN = derive), depth m */
+    const double* au;       /* [au_layers*n_cells] layer-major: upslope area m2 [, n cells draining in, n cells draining out] */
+    int32_t au_layers;      /* 1 (length(Au)==1 branch, splash.point.R:106-110) or 3 (:111-115) */
+    int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE: applies to every pointer above except year/doy/month (always host) */
+    int32_t forcing_dtype;  /* SPLASH_F64 (what R passes) or SPLASH_F32 (rasters are FLT4S on disk) */
+    int32_t reserved;
+} splash_grid_in;
+
+/* Outputs: the nine layers of R/splash.grid.R:449 (any pointer may be NULL = not wanted). */
+typedef struct splash_grid_out {
+    int64_t n_out;          /* layers the caller allocated: n_days, or splash_count_months() when monthly_out */
+    int64_t cell_stride;    /* elements between consecutive layers; 0 means n_cells */
+    double* wn;             /* soil water content, mm */
+    double* ro;             /* runoff, mm */
+    double* pet;            /* potential evapotranspiration, mm */
+    double* aet;            /* actual evapotranspiration, mm */
+    double* snow;           /* snow water equivalent, mm */
+    double* cond;           /* condensation, mm */
+    double* bflow;          /* lateral drainage, mm */
+    double* netr;           /* daytime net radiation, MJ m-2 */
+    double* sm_lim;         /* relative soil moisture limitation 0..1 */
+    double* state_final;    /* optional [5*n_cells] layer-major: wn, snow, qin, td, nd after the last day (resume state, SPLASH.cpp:1833-1835) */
+    double* cell_diag;      /* optional [SPLASH_NDIAG*n_cells] layer-major */
+    int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE for every pointer above */
+    int32_t reserved;
+} splash_grid_out;
+
+typedef struct splash_opts {
+    int32_t monthly_out;    /* sim.control$monthly_out, R/splash.grid.R:28,173-181: 1 = monthly mean(wn,snow,sm_lim)/sum(rest) */
+    int32_t max_spin;       /* spin-up pass limit; 0 means the reference's 1000 (SPLASH.cpp:1697) */
+    double spin_tol_mm;     /* spin-up tolerance on |delta wn(day 1)|; 0 means the reference's 1.0 mm */
+    int64_t tile_cells;     /* cells per device tile; 0 = choose from free device memory */
+    int32_t skip_spinup;    /* 1 = start run_all from state_init instead of spinning up (resume) */
+    int32_t reserved;
+    const double* state_init; /* [5*n_cells] layer-major wn, snow, qin, td, nd (host); used when skip_spinup */
+} splash_opts;
+
+/* Timing / accounting of the last call, filled by splash_last_stats (all times in milliseconds). */
+typedef struct splash_stats {
+    double h2d_ms;          /* host->device copies (sum over tiles, stream time) */
+    double setup_ms;        /* cell-setup + snow-threshold kernels */
+    double spinup_ms;       /* spin-up kernels */
+    double main_ms;         /* daily-integration kernel(s) */
+    double d2h_ms;          /* device->host copies */
+    double total_ms;        /* wall clock of the call */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t spin_cell_days; /* cell-days executed in spin-up (incl. check days) */
+    int64_t main_cell_days; /* n_cells * n_days */
+    int64_t kernel_launches;/* kernels of this library launched by the call */
+    int64_t unconverged_cells; /* cells that hit the pass limit */
+    int64_t n_tiles;
+    int64_t reserved;
+} splash_stats;
+
+int splash_abi_version(void);
+
+/* Create a context on CUDA device `device` (ordinal).  Fails with SPLASH_ERR_NO_DEVICE when there
+ * is no CUDA device: the library has no host implementation of the model. */
+int splash_ctx_create(int device, splash_ctx** out_ctx);
+void splash_ctx_destroy(splash_ctx* ctx);
+
+/* Message of the last failure on this context (or of the last failed splash_ctx_create when ctx is
+ * NULL).  Never NULL; valid until the next call on the same context. */
+const char* splash_last_error(const splash_ctx* ctx);
+
+/* Number of calendar-month groups in the day axis = length(ztime.months); what n_out must be for
+ * monthly_out (run-length of (year, month), like fastmatch::ctapply over format(time,'%Y-%m'),
+ * R/splash.point.R:208-211).  Pure host arithmetic. */
+int64_t splash_count_months(const int32_t* year, const int32_t* month, int64_t n_days);
+
+/* Run a block of cells.  Returns SPLASH_OK or an error code; on error outputs are unspecified. */
+int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts* opts, splash_grid_out* out);
+
+/* Run one cell: splash.point(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, ...).
+ * soil_data[6] as in splash_grid_in.soil; au has au_len (1 or 3) elements.  out is a splash_grid_out
+ * with n_cells = 1 semantics (host pointers). */
+int splash_point_run(splash_ctx* ctx, int64_t n_days, const int32_t* year, const int32_t* doy,
+                     const int32_t* month, const double* sw_in, const double* tc, const double* pn,
+                     double lat, double elev, double slop, double asp, const double* soil_data,
+                     const double* au, int32_t au_len, double resolution, const splash_opts* opts,
+                     splash_grid_out* out);
+
+/* Accounting of the last splash_grid_run / splash_point_run on this context. */
+int splash_last_stats(const splash_ctx* ctx, splash_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLASH_CUDA_H */
