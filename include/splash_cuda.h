@@ -146,7 +146,7 @@ typedef struct splash_stats {
     int64_t kernel_launches;/* kernels of this library launched by the call */
     int64_t unconverged_cells; /* cells that hit the pass limit */
     int64_t n_tiles;
-    int64_t reserved;
+    int64_t cycle_cells;    /* cells whose spin-up was cut short by exact cycle detection */
 } splash_stats;
 
 int splash_abi_version(void);

@@ -1,0 +1,16 @@
+"""rsplash_b200 -- B200-native engine for the splash.grid()/splash.point() hot path (SPLASH v2.0).
+
+The package is a thin host mirror of the reference's R interface over libsplash_cuda
+(include/splash_cuda.h).  Importing it does not need a GPU; running anything does.
+"""
+from . import _abi  # noqa: F401
+from ._abi import OUTPUT_NAMES  # noqa: F401
+
+__all__ = ["splash_grid", "splash_point", "Context", "SplashError", "OUTPUT_NAMES"]
+
+
+def __getattr__(name):
+    if name in ("splash_grid", "splash_point", "Context", "SplashError", "default_context"):
+        from . import api
+        return getattr(api, name)
+    raise AttributeError(name)

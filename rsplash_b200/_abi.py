@@ -103,7 +103,7 @@ class SplashStats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("unconverged_cells", C.c_int64),
         ("n_tiles", C.c_int64),
-        ("reserved", C.c_int64),
+        ("cycle_cells", C.c_int64),
     ]
 
     def as_dict(self):

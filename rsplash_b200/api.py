@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's R entry points for the hot path.
+
+`splash_point` and `splash_grid` keep the argument names and meaning of the R functions
+(reference R/splash.point.R:29, and the mapply() argument set of R/splash.grid.R:291-304) and
+return the same nine layers (R/splash.grid.R:449).  They only marshal numpy arrays into the C ABI
+(include/splash_cuda.h); all arithmetic happens in libsplash_cuda's CUDA kernels.
+
+What stays outside (as in the survey's scope table): raster I/O, terrain derivation (slope,
+aspect, upslope area, latitude, resolution are *inputs* here, as they are for splash.point), and
+the random monthly->daily rain disaggregation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._lib import Context, SplashError  # noqa: F401
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _f64(a, shape=None, name=""):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def splash_grid(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, time_index,
+                monthly_out: bool = True, ctx: Context | None = None, outputs: Sequence[str] = _abi.OUTPUT_NAMES,
+                return_state: bool = False, return_diag: bool = False, state_init=None, tile_cells: int = 0,
+                max_spin: int = 0, spin_tol_mm: float = 0.0) -> dict:
+    """Run a block of cells: the body of the reference's worker function `clFun`.
+
+    sw_in, tc, pn   [n_days, n_cells] daily forcing (float64, or float32 to use the f32 path)
+    lat, elev, slop, asp, resolution   [n_cells]
+    soil_data       [6, n_cells]  sand %, clay %, OM %, gravel %, bulk density (NaN = derive), depth m
+    Au              [n_cells] upslope area, or [3, n_cells] with the in/out neighbour counts
+    time_index      datetime64[D] axis of the forcing (n_days)
+    monthly_out     sim.control$monthly_out of splash.grid (default TRUE there)
+
+    Returns {layer: [n_out, n_cells]} for wn, ro, pet, aet, snow, cond, bflow, netr, sm_lim.
+    """
+    ctx = ctx or default_context()
+    sw_in = np.asarray(sw_in)
+    f32 = sw_in.dtype == np.float32
+    fdt = np.float32 if f32 else np.float64
+    sw_in = np.ascontiguousarray(sw_in, dtype=fdt)
+    if sw_in.ndim != 2:
+        raise ValueError("sw_in must be [n_days, n_cells]")
+    n_days, n_cells = sw_in.shape
+    tc = np.ascontiguousarray(tc, dtype=fdt)
+    pn = np.ascontiguousarray(pn, dtype=fdt)
+    if tc.shape != sw_in.shape or pn.shape != sw_in.shape:
+        raise ValueError("sw_in, tc and pn must have the same shape")
+    year, doy, month = _abi.time_axes(time_index)
+    if len(year) != n_days:
+        raise ValueError("time_index length does not match the forcing")
+    lat = _f64(lat, (n_cells,), "lat")
+    elev = _f64(elev, (n_cells,), "elev")
+    slop = _f64(slop, (n_cells,), "slop")
+    asp = _f64(asp, (n_cells,), "asp")
+    resolution = _f64(np.broadcast_to(np.asarray(resolution, dtype=np.float64), (n_cells,)), (n_cells,), "resolution")
+    soil = _f64(soil_data, (6, n_cells), "soil_data")
+    au = np.asarray(Au, dtype=np.float64)
+    if au.ndim == 1:
+        au = au[None, :]
+    au = _f64(au, name="Au")
+    if au.shape not in ((1, n_cells), (3, n_cells)):
+        raise ValueError("Au must be [n_cells] or [3, n_cells]")
+
+    n_out = _abi.count_months(year, month) if monthly_out else n_days
+    cin = _abi.SplashGridIn()
+    cin.n_cells, cin.n_days, cin.cell_stride = n_cells, n_days, n_cells
+    cin.year = year.ctypes.data_as(_abi.c_int32_p)
+    cin.doy = doy.ctypes.data_as(_abi.c_int32_p)
+    cin.month = month.ctypes.data_as(_abi.c_int32_p)
+    cin.sw_in, cin.tc, cin.pn = _ptr(sw_in), _ptr(tc), _ptr(pn)
+    cin.lat, cin.elev, cin.slop, cin.asp, cin.resolution = _ptr(lat), _ptr(elev), _ptr(slop), _ptr(asp), _ptr(resolution)
+    cin.soil, cin.au, cin.au_layers = _ptr(soil), _ptr(au), au.shape[0]
+    cin.mem_kind = _abi.SPLASH_MEM_HOST
+    cin.forcing_dtype = _abi.SPLASH_F32 if f32 else _abi.SPLASH_F64
+
+    result = {}
+    cout = _abi.SplashGridOut()
+    cout.n_out, cout.cell_stride, cout.mem_kind = n_out, n_cells, _abi.SPLASH_MEM_HOST
+    for k in outputs:
+        if k not in _abi.OUTPUT_NAMES:
+            raise ValueError(f"unknown output layer {k!r}")
+        result[k] = np.empty((n_out, n_cells), dtype=np.float64)
+        setattr(cout, k, _ptr(result[k]))
+    if return_state:
+        result["state_final"] = np.empty((5, n_cells))
+        cout.state_final = _ptr(result["state_final"])
+    if return_diag:
+        result["cell_diag"] = np.empty((_abi.SPLASH_NDIAG, n_cells))
+        cout.cell_diag = _ptr(result["cell_diag"])
+
+    opts = _abi.SplashOpts()
+    opts.monthly_out = int(bool(monthly_out))
+    opts.tile_cells = int(tile_cells)
+    opts.max_spin = int(max_spin)
+    opts.spin_tol_mm = float(spin_tol_mm)
+    if state_init is not None:
+        st = _f64(state_init, (5, n_cells), "state_init")
+        opts.skip_spinup, opts.state_init = 1, _ptr(st)
+    ctx.grid_run(cin, opts, cout)
+    result["stats"] = ctx.stats()
+    return result
+
+
+def splash_point(sw_in, tc, pn, lat, elev, slop=0.0, asp=0.0, soil_data=None, Au=0.0, resolution=250.0,
+                 time_index=None, monthly_out: bool = False, ctx: Context | None = None, **kw) -> dict:
+    """splash.point(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, time_index, monthly_out).
+
+    One cell; same defaults as the R function (R/splash.point.R:29).  Returns {layer: [n_out]}.
+    """
+    if soil_data is None or time_index is None:
+        raise ValueError("soil_data and time_index are required")
+    au = np.atleast_1d(np.asarray(Au, dtype=np.float64))
+    if au.size not in (1, 3):
+        raise ValueError("Au must have 1 or 3 elements")
+    col = lambda a: np.asarray(a, dtype=np.float64).reshape(-1, 1)
+    res = splash_grid(col(sw_in), col(tc), col(pn), [lat], [elev], [slop], [asp],
+                      np.asarray(soil_data, dtype=np.float64).reshape(6, 1), au.reshape(-1, 1), [resolution],
+                      time_index, monthly_out=monthly_out, ctx=ctx, **kw)
+    return {k: (v[:, 0] if isinstance(v, np.ndarray) and v.ndim == 2 else v) for k, v in res.items()}

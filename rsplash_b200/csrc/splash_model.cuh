@@ -1,0 +1,833 @@
+// splash_model.cuh -- device-side SPLASH v2.0 cell model for sm_100a (FP64 CUDA cores).
+//
+// One thread owns one cell.  Per-cell constants live in shared memory as private columns
+// (cc[k * blockDim.x + threadIdx.x]: conflict-free, no synchronisation), the five state scalars
+// (wn, snow, qin, td, nd) stay in registers across the day loop.
+//
+// What is restated here (reference paths relative to /root/reference):
+//   cell_setup()      R/splash.point.R:96-115 (soil_info) + soil_hydro :232-416, the per-cell
+//                     invariants of SPLASH::run_one_day (src/SPLASH.cpp:946-1029, 1291-1356),
+//                     EVAP::elv2pres (src/EVAP.cpp:319-336), SOLAR tau_o (src/SOLAR.cpp:170)
+//   lateral_consts()  the terms of run_one_day that depend on `cellout`, which R overwrites with
+//                     the aridity index between the two spin-ups (R/splash.point.R:150)
+//   snow_prob_z()     snowfall_prob, R/splash.point.R:560-578
+//   splash_day()      one day: snow partition (R/splash.point.R:120-128,547-555), then
+//                     SOLAR::calculate_daily_fluxes (src/SOLAR.cpp:129-255),
+//                     EVAP::calculate_daily_fluxes (src/EVAP.cpp:100-263),
+//                     SPLASH::run_one_day (src/SPLASH.cpp:984-1583) incl. moist_surf (:1921-1961)
+//                     and inf_GA (:1963-2023)
+//
+// Numerics: the arithmetic follows the reference's expression shapes and evaluation order; the
+// file is compiled with -fmad=false (the reference build has no FMA contraction, SURVEY B-9).
+// Hoisting is limited to sub-expressions whose value is bit-identical when computed once
+// (same operands, same operation order).  Differences against the CPU reference therefore come
+// from libdevice vs glibc transcendentals only (<= 2 ulp each).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace splash {
+
+// ------------------------------------------------------------------------------------------------
+// Global constants, reference src/global.cpp:51-82
+// ------------------------------------------------------------------------------------------------
+constexpr double kA = 91.86328;
+constexpr double kalb_sw = 0.30;
+constexpr double kb = 0.2012435;
+constexpr double kc = 0.25;
+constexpr double kd = 0.50;
+constexpr double kkfus = 334000;
+constexpr double kG = 9.80665;
+constexpr double kGsc = 1360.8;
+constexpr double kL = 0.0065;
+constexpr double kMa = 0.028963;
+constexpr double kMv = 0.01802;
+constexpr double kPo = 101325;
+constexpr double kR = 8.31447;
+constexpr double kTo = 288.15;
+constexpr double kPI = 3.141592653589793;
+constexpr double kpir = (kPI / 180.0);
+constexpr double kfluidity = 35187037;
+
+// ------------------------------------------------------------------------------------------------
+// Per-cell constant slots (rows of the [NCC][pitch] constant matrix)
+// ------------------------------------------------------------------------------------------------
+enum CellConst : int {
+    // snow partition
+    C_ELEV_K = 0,  // elev * 0.0004596581
+    C_LAT_K,       // |lat| * 0.0110592101
+    C_TT,          // threshold temperature Tt (written by the snow-threshold kernel)
+    // geometry
+    C_COS_LAT, C_SIN_LAT, C_SIN_S, C_COS_S, C_COS_A, C_SIN_A, C_TAN_S, C_COS2_S,
+    // atmosphere
+    C_TAU_O, C_TAU_A, C_TAU_B, C_PATM, C_PBAR, C_PBARF, C_VISC0,
+    // soil column
+    C_SAT, C_RES, C_DEPTH, C_D1000, C_THS, C_THR, C_DTH, C_ILAM, C_NLAM, C_E3, C_BUB, C_BP10,
+    C_WMAX, C_WMR, C_THWMAX, C_INTPERM, C_HF, C_KUEXP,
+    // lateral flow
+    C_BRQ0, C_DENKB, C_BRW, C_ACSW, C_CW, C_SIDOCT, C_AI, C_AU,
+    C_CELLOUT, C_CQ0, C_ACSQS, C_CT,  // depend on cellout (recomputed after the aridity pass)
+    // output stage
+    C_WRR,         // Wmax_R - RES, denominator of sm_lim (R/splash.point.R:197)
+    NCC
+};
+
+struct DayTab {      // per-day values that do not depend on the cell (host-built, SOLAR.cpp:98-124)
+    double dr;       // distance factor
+    double sd;       // sin(delta*pir)
+    double cd;       // cos(delta*pir)
+    int32_t month;   // 0..11
+    int32_t group;   // month-group id of the day (monthly output)
+};
+
+struct MonthTab {    // frain_func's month factors (R/splash.point.R:549-550), host-built
+    double s1[12];   // dsin((m+2)/1.91)
+    double trm14[12];// 1.4 * (13.3*(0.55+dsin(m+4))*0.6)
+};
+
+struct CellState {
+    double wn, snow, qin, td, nd;
+};
+
+struct DayOut {
+    double ro, pet, aet, cond, bflow, netr;
+};
+
+// std::max / std::min semantics of the reference (NaN in the first argument wins, SURVEY B-1)
+__device__ __forceinline__ double cxx_max(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double cxx_min(double a, double b) { return (b < a) ? b : a; }
+
+// ------------------------------------------------------------------------------------------------
+// glibc expf, bit-exact.  EVAP::calc_viscosity_h2o ends in std::exp(float) (src/EVAP.cpp:451),
+// i.e. glibc's expf, whose result differs from the correctly rounded one in a fraction of a
+// percent of arguments; viscosity scales every conductivity, so a 1-ulp float error (6e-8) would
+// dominate the error budget (SURVEY B-4).  This follows the published algorithm of glibc 2.28+
+// (sysdeps/ieee754/flt-32/e_expf.c, N = 32 table, degree-3 polynomial in double) with the FMA
+// contraction pattern of the x86-64 `-mfma` build that the ifunc selects on the CPUs used here.
+// ------------------------------------------------------------------------------------------------
+__device__ __constant__ double kExp2Tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+__device__ __forceinline__ float glibc_expf(float x) {
+    const double xd = (double)x;
+    if (!(fabsf(x) < 88.0f)) return (float)exp(xd);  // overflow/underflow/NaN tails: not reached by viscosity
+    const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
+    double kd = fma(InvLn2N, xd, Shift);
+    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd = kd - Shift;
+    const double r = fma(InvLn2N, xd, -kd);
+    const double z = fma(r, C0, C1);
+    const double r2 = r * r;
+    double y = fma(r, C2, 1.0);
+    y = fma(z, r2, y);
+    const uint64_t i = ki & 31u;
+    const uint64_t t = (uint64_t)__double_as_longlong(kExp2Tab[i]) - (i << 47) + (ki << 47);
+    y = y * __longlong_as_double((long long)t);
+    return (float)y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EVAP helpers
+// ------------------------------------------------------------------------------------------------
+struct DensityPoly {
+    double po, ko, ca, cb;
+};
+
+// temperature polynomials of EVAP::density_h2o, src/EVAP.cpp:349-378 (power sums as written)
+__device__ __forceinline__ DensityPoly density_poly(double tc) {
+    DensityPoly q;
+    double po = 0.99983952;
+    po += (6.788260e-5) * tc;
+    po += -(9.08659e-6) * tc * tc;
+    po += (1.022130e-7) * tc * tc * tc;
+    po += -(1.35439e-9) * tc * tc * tc * tc;
+    po += (1.471150e-11) * tc * tc * tc * tc * tc;
+    po += -(1.11663e-13) * tc * tc * tc * tc * tc * tc;
+    po += (5.044070e-16) * tc * tc * tc * tc * tc * tc * tc;
+    po += -(1.00659e-18) * tc * tc * tc * tc * tc * tc * tc * tc;
+    double ko = 19652.17;
+    ko += 148.1830 * tc;
+    ko += -2.29995 * tc * tc;
+    ko += 0.01281 * tc * tc * tc;
+    ko += -(4.91564e-5) * tc * tc * tc * tc;
+    ko += (1.035530e-7) * tc * tc * tc * tc * tc;
+    double ca = 3.26138;
+    ca += (5.223e-4) * tc;
+    ca += (1.324e-4) * tc * tc;
+    ca += -(7.655e-7) * tc * tc * tc;
+    ca += (8.584e-10) * tc * tc * tc * tc;
+    double cb = (7.2061e-5);
+    cb += -(5.8948e-6) * tc;
+    cb += (8.69900e-8) * tc * tc;
+    cb += -(1.0100e-9) * tc * tc * tc;
+    cb += (4.3220e-12) * tc * tc * tc * tc;
+    q.po = po;
+    q.ko = ko;
+    q.ca = ca;
+    q.cb = cb;
+    return q;
+}
+
+// pressure part of EVAP::density_h2o, src/EVAP.cpp:381-388 (pbar = 1e-5 * p)
+__device__ __forceinline__ double density_at(const DensityPoly& q, double pbar) {
+    const double num = (q.ko + q.ca * pbar + q.cb * (pbar * pbar));
+    double pw = num;
+    pw /= (num - pbar);
+    pw *= (1.0e3) * q.po;
+    return pw;
+}
+
+// EVAP::calc_viscosity_h2o, src/EVAP.cpp:405-462, with its FP32 roundings.  `tcf` is the float
+// the reference narrows tw to, `rho_d` = density_h2o((double)tcf, (double)pf) in double.
+__device__ __forceinline__ double viscosity_h2o(float tcf, double rho_d) {
+    const float tk_ast = 647.096f;
+    const float rho = (float)rho_d;
+    const float tbar = (float)(((double)tcf + 273.15) / (double)tk_ast);
+    const float tbarx = (float)sqrt((double)tbar);  // pow(tbar, 0.5) in double, narrowed
+    const float tbar2 = tbar * tbar;
+    const float tbar3 = tbar * tbar * tbar;
+    const float rbar = rho / 322.0f;
+    float mu0 = (float)(1.67752 + 2.20462 / (double)tbar + 0.6366564 / (double)tbar2 - 0.241605 / (double)tbar3);
+    mu0 = (float)(1e2 * (double)tbarx / (double)mu0);
+    const float ctbar = (float)((1.0 / (double)tbar) - 1.0);
+    // integer powers of (rbar - 1.0) in double, j = 0..6
+    const double rb = (double)rbar - 1.0;
+    const double rb2 = rb * rb, rb3 = rb2 * rb, rb4 = rb3 * rb, rb5 = rb4 * rb, rb6 = rb5 * rb;
+    // integer powers of ctbar in double narrowed to float, i = 0..5
+    const double ct = (double)ctbar;
+    const double ct2 = ct * ct, ct3 = ct2 * ct, ct4 = ct3 * ct, ct5 = ct4 * ct;
+    // coef2_i = sum_j h[j][i] * (rbar-1)^j, accumulated in the reference's order with a float
+    // round after every add; the table's zero entries add an exact 0 and are skipped.
+#define SPLASH_H(acc, h, p) acc = (float)((double)(acc) + (double)(h) * (p))
+    float c2_0 = 0.0f, c2_1 = 0.0f, c2_2 = 0.0f, c2_3 = 0.0f, c2_4 = 0.0f, c2_5 = 0.0f;
+    SPLASH_H(c2_0, 0.520094f, 1.0); SPLASH_H(c2_0, 0.222531f, rb); SPLASH_H(c2_0, -0.281378f, rb2);
+    SPLASH_H(c2_0, 0.161913f, rb3); SPLASH_H(c2_0, -0.0325372f, rb4);
+    SPLASH_H(c2_1, 0.0850895f, 1.0); SPLASH_H(c2_1, 0.999115f, rb); SPLASH_H(c2_1, -0.906851f, rb2);
+    SPLASH_H(c2_1, 0.257399f, rb3);
+    SPLASH_H(c2_2, -1.08374f, 1.0); SPLASH_H(c2_2, 1.88797f, rb); SPLASH_H(c2_2, -0.772479f, rb2);
+    SPLASH_H(c2_3, -0.289555f, 1.0); SPLASH_H(c2_3, 1.26613f, rb); SPLASH_H(c2_3, -0.489837f, rb2);
+    SPLASH_H(c2_3, 0.0698452f, rb4); SPLASH_H(c2_3, -0.00435673f, rb6);
+    SPLASH_H(c2_4, -0.257040f, rb2); SPLASH_H(c2_4, 0.00872102f, rb5);
+    SPLASH_H(c2_5, 0.120573f, rb); SPLASH_H(c2_5, -0.000593264f, rb6);
+#undef SPLASH_H
+    float mu1 = 0.0f;
+    mu1 = __fadd_rn(mu1, __fmul_rn(1.0f, c2_0));         // pow(ctbar, 0) == 1
+    mu1 = __fadd_rn(mu1, __fmul_rn((float)ct, c2_1));
+    mu1 = __fadd_rn(mu1, __fmul_rn((float)ct2, c2_2));
+    mu1 = __fadd_rn(mu1, __fmul_rn((float)ct3, c2_3));
+    mu1 = __fadd_rn(mu1, __fmul_rn((float)ct4, c2_4));
+    mu1 = __fadd_rn(mu1, __fmul_rn((float)ct5, c2_5));
+    mu1 = glibc_expf(__fmul_rn(rbar, mu1));
+    const float mu_bar = __fmul_rn(mu0, mu1);
+    const float mu = __fmul_rn(mu_bar, 1e-6f);
+    return (double)mu;
+}
+
+// EVAP::specific_heat, src/EVAP.cpp:491-515
+__device__ __forceinline__ double specific_heat(double tc) {
+    double cp;
+    if (tc < 0) {
+        cp = 1004.5714270;
+    } else if (tc > 100) {
+        cp = 2031.2260590;
+    } else {
+        cp = 1.0045714270;
+        cp += (2.050632750e-3) * tc;
+        cp += -(1.631537093e-4) * tc * tc;
+        cp += (6.212300300e-6) * tc * tc * tc;
+        cp += -(8.830478888e-8) * tc * tc * tc * tc;
+        cp += (5.071307038e-10) * tc * tc * tc * tc * tc;
+        cp *= (1.0e3);
+    }
+    return cp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Brooks-Corey column transmittance: the block repeated at src/SPLASH.cpp:1406-1426 and
+// :1511-1531.  Returns T_uns (after the flux-density scaling and the <0/NaN failsafe) and Acs_out.
+// ------------------------------------------------------------------------------------------------
+struct Transm {
+    double t_uns, acs_out;
+};
+
+template <class CC>
+__device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, double ksat_visc) {
+    const double bub = cc(C_BUB);
+    const double e3 = cc(C_E3);
+    const double depth = cc(C_DEPTH);
+    const double theta_i = (sm) / cc(C_D1000);
+    const double psi_m = bub / pow((((theta_i - cc(C_THR)) / cc(C_DTH))), cc(C_ILAM));
+    double wtd = ((bub - psi_m) / 1000.0);
+    if (wtd < 0.0 || isnan(wtd)) {
+        wtd = 0.01;
+    } else if (wtd > depth) {
+        wtd = depth;
+    }
+    Transm r;
+    r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
+    double t_uns = (ksat_visc * bub / e3) * (pow((bub / psi_m), e3) - pow((bub / (psi_m + (wtd * 1000.0))), e3));
+    t_uns *= cc(C_CT);
+    if (t_uns < 0.0 || isnan(t_uns)) {
+        t_uns = 0.0;
+    }
+    r.t_uns = t_uns;
+    return r;
+}
+
+// snowfall_prob's exponent, R/splash.point.R:576
+template <class CC>
+__device__ __forceinline__ double snow_prob(const CC& cc, double tc) {
+    return 1 / (1 + exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// One day of one cell.
+//   cc     accessor for the cell's constants
+//   dt     day table entry (dr, sin/cos of declination, month)
+//   mt     month table of frain_func
+//   sw_in, tc, pn   raw forcing of the day (pn = total precipitation before the snow partition)
+//   st     state in/out
+//   o      fluxes of the day
+//   snowfall_out    snowfall of the day (for the aridity index and the occurrence flags)
+//   rain_out        rainfall of the day
+// ------------------------------------------------------------------------------------------------
+template <class CC>
+__device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
+                                           double pn, CellState& st, DayOut& o, double& rain_out,
+                                           double& snowfall_out) {
+    // ---- snow partition, R/splash.point.R:120-128 with frain_func :547-555 ------------------------
+    const double p_snow = snow_prob(cc, tc);
+    double f_rain;
+    if (isnan(p_snow)) {
+        f_rain = p_snow;  // ifelse(NA, ., .) is NA
+    } else if (p_snow >= 0.5) {
+        const double Tt = cc(C_TT);
+        const double Ttm = Tt + (Tt * mt.s1[dt.month]);
+        const double x = (tc - Ttm) / (mt.trm14[dt.month]);
+        double frain;
+        if (tc <= Ttm) {
+            frain = 5 * (x * x * x) + 6.76 * (x * x) + 3.19 * x + 0.5;
+        } else {
+            frain = 5 * (x * x * x) - 6.76 * (x * x) + 3.19 * x + 0.5;
+        }
+        if (frain < 0) frain = 0;
+        if (frain > 1) frain = 1;
+        f_rain = frain;
+    } else {
+        f_rain = 1;
+    }
+    const double snowfall = pn * (1 - f_rain);
+    const double rain = pn * f_rain;
+    snowfall_out = snowfall;
+    rain_out = rain;
+
+    const double wn = st.wn;
+    // ---- 00/03. theta_i clamp and supply rate, SPLASH.cpp:984-990, 1042-1048 ----------------------
+    const double theta_s = cc(C_THS);
+    double theta_i = (wn) / cc(C_D1000);
+    if (theta_i >= theta_s) {
+        theta_i = theta_s - 0.001;
+    } else if (theta_i <= cc(C_THR)) {
+        theta_i = cc(C_THR) + 0.001;
+    }
+    double sw = ((wn - cc(C_RES)) / cc(C_WMR));
+    if (sw < 0.0 || isnan(sw)) {
+        sw = 0.0;
+    } else if (sw > 1.0) {
+        sw = 1.0;
+    }
+    // ---- 04. snowpack, :1225-1231 ---------------------------------------------------------------
+    double nd = st.nd;
+    if (snowfall > 0.0) {
+        nd = 0.0;
+    } else {
+        nd += 1.0;
+    }
+    double snow = st.snow + snowfall;
+
+    // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:129-255 ------------------------------------------
+    const double a = dt.sd * cc(C_COS_LAT) * cc(C_SIN_S) * cc(C_COS_A) - dt.sd * cc(C_SIN_LAT) * cc(C_COS_S);
+    const double b = dt.cd * cc(C_COS_LAT) * cc(C_COS_S) + dt.cd * cc(C_SIN_LAT) * cc(C_SIN_S) * cc(C_COS_A);
+    const double c = dt.cd * cc(C_SIN_S) * cc(C_SIN_A);
+    const double d = b * b + c * c - a * a;
+    double sinfirst;
+    if (d < 0) {
+        sinfirst = (a * c) / (b * b + c * c);
+    } else {
+        sinfirst = (a * c + b * sqrt(d)) / (b * b + c * c);
+    }
+    const double ru = -1 * a + c * sinfirst;
+    const double rv = b;
+    double hs;
+    const double ruv = ru / rv;
+    if (ruv >= 1.0) {
+        hs = 180.0;
+    } else if (ruv <= -1.0) {
+        hs = 0.0;
+    } else {
+        hs = -1.0 * ruv;
+        hs = acos(hs);
+        hs /= kpir;
+    }
+    const double sin_hs = sin(hs * kpir);
+    double ra_d = (86400.0 / kPI) * dt.dr * kGsc;
+    ra_d *= (ru * hs * kpir + rv * sin_hs);
+    const double tau_o = cc(C_TAU_O);
+    const double r_in = 86400 * sw_in;
+    double tau;
+    if (isnan(ra_d) || r_in == 0 || ra_d < r_in) {
+        tau = tau_o;
+    } else {
+        tau = r_in / (ra_d);
+    }
+    double sf = pow(((tau - cc(C_TAU_A)) / cc(C_TAU_B)), (1 / 0.7410));
+    if (isnan(sf)) {
+        sf = 0.0;
+    } else if (sf > 1.0) {
+        sf = 1.0;
+    }
+    const double rnl = (0.0883289 + (1.0 - kb) * sf) * (kA + 1.95974 * tc);
+    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * exp(-0.895189 * nd));
+    const double sfc = snow / (140.0 + snow);
+    const double alb_v = kalb_sw - 0.17 * sw;
+    const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
+    double rw;
+    if ((sw_in == 0.0) || (hs == 0.0)) {
+        rw = (1.0 - alb) * tau * dt.dr * kGsc;
+    } else {
+        rw = (1.0 - alb) * (r_in) / ((86400.0 / kPI) * (ru * kpir * hs + rv * sin_hs));
+    }
+    double hn;
+    const double qn = (rnl - rw * ru) / (rw * rv);
+    if (qn >= 1.0) {
+        hn = 0;
+    } else if (qn <= -1.0) {
+        hn = 180.0;
+    } else {
+        hn = acos(qn);
+        hn /= kpir;
+    }
+    const double sin_hn = sin(hn * kpir);
+    double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
+    rn_d *= (86400.0 / kPI);
+    double rnn_d = rw * rv * (sin_hs - sin_hn);
+    rnn_d += rw * ru * (hs - hn) * kpir;
+    rnn_d -= rnl * (kPI - hn * kpir);
+    rnn_d *= (86400.0 / kPI);
+
+    // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:100-263 --------------------------------------------
+    const double patm = cc(C_PATM);
+    double s = exp((tc * 17.269) / (tc + 237.3));  // sat_slope, :299-301
+    s /= ((tc + 237.3) * (tc + 237.3));
+    s *= (17.269) * (237.3) * (610.78);
+    double lv = (tc + 273.15) / (tc + 273.15 - 33.91);  // enthalpy_vap, :313-315
+    lv = lv * lv;
+    lv *= 1.91846e6;
+    const DensityPoly qd = density_poly(tc);
+    const double pw = density_at(qd, cc(C_PBAR));
+    const double cp = specific_heat(tc);
+    const double g = (kMa * cp * patm) / (kMv * lv);  // psychro, :486
+    const double econ = s / (lv * pw * (s + g));
+    // viscosity at tw = max(tc, 0) narrowed to float, :100-105,120,413
+    double visc;
+    if (tc < 0.0) {
+        visc = cc(C_VISC0);  // tw == 0: a function of the cell's pressure only
+    } else {
+        const float tcf = (float)tc;
+        double rho_d;
+        if ((double)tcf == tc) {
+            rho_d = density_at(qd, cc(C_PBARF));  // same temperature polynomials, float-rounded pressure
+        } else {
+            rho_d = density_at(density_poly((double)tcf), cc(C_PBARF));
+        }
+        visc = viscosity_h2o(tcf, rho_d);
+    }
+    const double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
+    const double eet_d = (1.0e3) * (s / (lv * pw * (s + 0.24 * g))) * rn_d;
+    const double rx = (3.6e6) * econ;
+    const double pet_max = rx * ((rw * (ru + rv)) - rnl);
+    const double B_r = g / (sw * s);
+    const double EF = 1 / (B_r + 1.0);
+    double swp = pet_max * EF;
+    if (swp < 0.0 || isnan(swp)) {
+        swp = 0.0;
+    }
+    const double cos_hi = swp / (rw * rv * rx) + rnl / (rw * rv) - ru / rv;
+    double hi;
+    if (cos_hi >= 1.0) {
+        hi = 0.0;
+    } else if (cos_hi <= -1.0) {
+        hi = 180.0;
+    } else {
+        hi = acos(cos_hi);
+        hi /= kpir;
+    }
+    double snowmelt_tot;
+    if (tc >= 3.0) {
+        snowmelt_tot = cxx_min(snow, (rn_d / (pw * kkfus)) * 1000.0);
+    } else {
+        snowmelt_tot = 0.0;
+    }
+    double melt_enrg = (snowmelt_tot / 1000) * pw * kkfus;
+    const double AE = rn_d - melt_enrg;
+    const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
+    melt_enrg += ((sublimation / 1000.0) / econ);
+    double aet_d = swp * hi * kpir;
+    aet_d += rx * rw * rv * (sin_hn - sin(hi * kpir));
+    aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
+    aet_d *= (24.0 / kPI);
+    aet_d -= (melt_enrg * econ * 1000.0);
+    if (aet_d < 0.0) {
+        aet_d = 0.0;
+    }
+
+    // ---- back in SPLASH::run_one_day, SPLASH.cpp:1236-1284 -----------------------------------------
+    snow -= snowmelt_tot;
+    const double snowmelt = snowmelt_tot - sublimation;
+    const double Ksat_visc = cc(C_INTPERM) * ((pw * kG) / visc) * 3.6;
+    const double inflow = rain + cn + snowmelt;
+    // moist_surf(depth, 10, bub, wn, SAT, RES, lambda), :1935-1957
+    double surf_moist;
+    {
+        const double theta_r = cc(C_THR);
+        const double bp = cc(C_BP10);
+        const double theta_mean = (wn) / cc(C_D1000);
+        const double water_pot_BC = bp / pow((((theta_mean - theta_r) / cc(C_DTH))), cc(C_ILAM));
+        const double total_head_BC = water_pot_BC + 10.0;
+        double theta_BC = cc(C_DTH) * pow((total_head_BC / bp), cc(C_NLAM)) + theta_r;
+        if (theta_mean < theta_r) {
+            theta_BC = theta_r;
+        } else if (isnan(theta_BC)) {
+            theta_BC = theta_s;
+        }
+        surf_moist = theta_BC;
+    }
+    const double theta_m = cxx_max(cc(C_THWMAX), theta_i);
+    // inf_GA(bub, surf_moist, Ksat_visc, theta_s, lambda, inflow, 6.0, slop), :1984-2022
+    double infi;
+    {
+        const double P = inflow;
+        const double r = P / 6.0;
+        const double h_f = cc(C_HF);
+        const double delta_theta = (theta_s - surf_moist);
+        double I = 0.0;
+        if (r <= Ksat_visc) {
+            I = P;
+        } else {
+            if (delta_theta <= 0.0) {
+                I = Ksat_visc * 6.0;
+            } else {
+                double tp = (Ksat_visc * delta_theta * -1.0 * h_f) / (r * (r - Ksat_visc));
+                if (tp <= 0.0 || isnan(tp)) {
+                    tp = 0.01;
+                }
+                const double tp_s = tp / cc(C_COS2_S);
+                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * log(1 - (r * tp_s / (h_f * delta_theta)))));
+            }
+        }
+        if (I > P) {
+            I = P;
+        }
+        infi = I;
+    }
+    const double ro_h = cxx_max(inflow - infi, 0.0);
+    double R = infi - aet_d;
+    const double Kunsat = Ksat_visc * pow((theta_m / theta_s), cc(C_KUEXP));
+    const double hyd_grad_in = cc(C_TAN_S);
+    const double hyd_grad_z = (infi / (Ksat_visc * 24)) - 1.0;
+    const double hyd_grad_out = sqrt((hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in));
+
+    // ---- 5.2.1 recession constant, :1303-1326 ------------------------------------------------------
+    const double kbe3 = (Ksat_visc * cc(C_BUB) / cc(C_E3));
+    const double T_q0 = kbe3 * cc(C_BRQ0);
+    const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
+    const double Q_qs = (hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS) / 1000.0);
+    const double Kb = exp((Q_q0 - Q_qs) / cc(C_DENKB));
+    // ---- 5.2.2 drainage at Wmax, :1346-1360 --------------------------------------------------------
+    const double To_uns = kbe3 * cc(C_BRW);
+    const double Qo_uns = To_uns * cc(C_CW);
+    const double Qo_sat = Ksat_visc * 24.0 * cc(C_ACSW) / 1000.0;
+    const double Qt = (Qo_sat + Qo_uns) * hyd_grad_out;
+    // ---- 5.2.3 upslope input of the previous day, :1365-1372 ---------------------------------------
+    double q_in_o = 0.0;
+    if ((st.td <= 0.0) || (st.qin <= 0.0)) {
+        q_in_o = 0.0;
+    } else {
+        q_in_o = st.qin * Kb;
+    }
+    // ---- 5.3/5.4 soil moisture and Dunne runoff, :1377-1397 ----------------------------------------
+    const double SAT = cc(C_SAT), RES = cc(C_RES);
+    double sm = wn + q_in_o + R;
+    double ro_d = 0.0;
+    if (sm > SAT) {
+        ro_d = (sm - SAT);
+        sm = SAT;
+        if (R > 0) {
+            R -= ro_d;
+        }
+    } else if (sm < RES) {
+        sm = RES;
+        ro_d = 0.0;
+    }
+    // ---- 5.6 transmittance after recharge, :1406-1457 ----------------------------------------------
+    const bool deep = (cc(C_DEPTH) >= 2.0);
+    const double Ai = cc(C_AI);
+    Transm tr = column_transmittance(cc, sm, Ksat_visc);
+    double T;
+    {
+        double T_uns = tr.t_uns;
+        double T_sat;
+        if (deep) {
+            T_uns += Kunsat * 24.0;
+            T_sat = Ksat_visc * 24.0 * ((tr.acs_out + Ai) / Ai);
+        } else {
+            T_sat = Ksat_visc * 24.0 * (tr.acs_out / Ai);
+        }
+        T = (T_sat + T_uns) * hyd_grad_out;
+    }
+    const double Q = (T * Ai) / 1000;
+    // ---- 5.7 same-day upslope input, :1465-1483 ----------------------------------------------------
+    double t_drain = 0.0;
+    double q_in_f = 0.0;
+    const double td = st.td - 1.0;
+    if ((R > 0.0) && (sm > cc(C_WMAX))) {
+        const double lkb = log(Kb);
+        const double Au = cc(C_AU);
+        t_drain = -1.0 * log(1.0 - (lkb * (Au * R / Q))) / lkb;
+        q_in_f = (Qt - Au * R * lkb) / Ai;
+    }
+    if (q_in_f < 0.0 || isnan(q_in_f)) {
+        q_in_f = 0.0;
+    }
+    const double tdrain_out = cxx_max((td + t_drain) / 2, 0.0);
+    // ---- 5.8 update soil moisture, :1488-1506 ------------------------------------------------------
+    const double sm_before = sm;
+    sm += (q_in_f);
+    if (sm > SAT) {
+        ro_d += (sm - SAT);
+        sm = SAT;
+    } else if (sm < RES) {
+        sm = RES;
+    }
+    const double ro = ro_d + ro_h;
+    // ---- 5.6' transmittance after upslope input, :1511-1547.  When sm did not move the block
+    //      recomputes exactly the values of 5.6, so they are reused (bit-identical). -----------------
+    if (!(sm == sm_before)) {
+        tr = column_transmittance(cc, sm, Ksat_visc);
+    }
+    {
+        const double T_sat = Ksat_visc * 24.0 * (tr.acs_out / Ai);
+        T = (T_sat + tr.t_uns) * hyd_grad_out;
+    }
+    // ---- 5.8' drain, :1552-1567 --------------------------------------------------------------------
+    sm -= (T);
+    if (sm > SAT) {
+        sm = SAT;
+    } else if (sm < RES) {
+        sm = RES;
+    }
+    // ---- 5.9 next-day input and outputs, :1573-1583, 1898-1908 -------------------------------------
+    st.wn = sm;
+    st.snow = snow;
+    st.qin = cxx_max(cxx_max(q_in_o, q_in_f), 0.0);
+    st.td = tdrain_out;
+    st.nd = nd;
+    o.ro = ro;
+    o.pet = eet_d;
+    o.aet = aet_d;
+    o.cond = cn;
+    o.bflow = T;
+    o.netr = rn_d / 1e6;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Terms of run_one_day that depend on `cellout` (SPLASH.cpp:1305, 1319, 1420, 1426).
+// ------------------------------------------------------------------------------------------------
+template <class CC>
+__device__ __forceinline__ void lateral_consts(CC& cc, double cellout) {
+    const double sid_oct = cc(C_SIDOCT);
+    cc(C_CELLOUT) = cellout;
+    cc(C_CQ0) = ((24.0 * sid_oct * cellout) / (1.0e6));
+    cc(C_ACSQS) = (cc(C_DEPTH)) * sid_oct * cellout;
+    cc(C_CT) = ((24.0 * cellout * sid_oct) / (1000.0 * cc(C_AI)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-shot per-cell setup: pedotransfer functions, soil_info, and every per-cell invariant of the
+// day step.  Inputs as in splash_grid_in (raw user values).
+// ------------------------------------------------------------------------------------------------
+struct CellInputs {
+    double lat, elev, slop, asp, resolution;
+    double sand, clay, om, gravel, bd, depth;
+    double au, cellin, cellout;
+};
+
+struct CellDiag {
+    double sat, wp, fc, ksat, lambda, depth, bub, res, wmax_r;
+};
+
+template <class CC>
+__device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDiag& dg) {
+    // ---- soil_hydro, R/splash.point.R:261-380, 410 -------------------------------------------------
+    const double fsand = in.sand / 100;
+    const double fclay = in.clay / 100;
+    const double fOM = in.om / 100;
+    const double fgravel = in.gravel / 100;
+    const double dp = 1 / ((fOM / 1.3) + ((1 - fOM) / 2.65));
+    double bd = in.bd;
+    if (isnan(bd)) {
+        bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
+    }
+    if (bd < 0.81) bd = 0.81;
+    double sat = 1 - (bd / dp);
+    const double sq_clay = sqrt(fclay);  // fclay^0.5
+    double fc = (sat / bd) * (0.4760944 + (0.9402962 - 0.4760944) * sq_clay) *
+                exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
+    const double wp_Ball = fc * (0.2018522 + (0.7809203 - 0.2018522) * sq_clay);
+    double wp = -2.464e-05 * in.sand + 3.650e-03 * in.clay + 8.680e-03 * in.om + 9.393e-03 * bd;
+    if (!isnan(wp) && wp >= fc) wp = wp_Ball;
+    const double coef_B = (log(1500.0) - log(33.0)) / (log(fc) - log(wp));
+    const double coef_A = exp(log(33.0) + coef_B * log(fc));
+    const double coef_lambda = 1 / coef_B;
+    const double coeff_c = 1000.0 / (997 * 9.80665);
+    const double theta_c = pow((coeff_c * coef_A / 2.0), (1 / (1 + coef_B)));
+    double theta_r0 = (0.0285 + 0.00336 * (in.clay)) * bd;
+    if (!isnan(theta_r0) && theta_r0 > wp) theta_r0 = wp;
+    sat = sat * (1 - fgravel);
+    fc = fc * (1 - fgravel);
+    wp = wp * (1 - fgravel);
+    const double ksat = 857.48454 / (1 + exp(-2.70927 * fsand + 3.62264 * bd + 7.33398 * fclay + -8.11795 * (sat - fc) +
+                                            18.75552 * fOM + 1.03319 * coef_lambda));
+    const double m33i = 0.278 * fsand + 0.034 * fclay + 0.022 * fOM - 0.018 * (fsand * fOM) - 0.027 * (fclay * fOM) -
+                        0.584 * (fsand * fclay) + 0.078;
+    const double m33 = m33i + (0.636 * m33i - 0.107);
+    const double bub_init = -21.6 * fsand - 27.93 * fclay - 81.97 * m33 + 71.12 * (fsand * m33) + 8.29 * (fclay * m33) +
+                            14.05 * (fsand * fclay) + 27.16;
+    double bubbling_p = bub_init + (0.02 * (bub_init * bub_init) - 0.113 * bub_init - 0.7);
+    bubbling_p = bubbling_p * -101.97162129779;
+    if (!isnan(bubbling_p) && bubbling_p > 0) bubbling_p = coef_A * -101.97162129779;
+    const double res_frac = theta_r0 * (1 - fgravel);
+
+    // ---- soil_info, R/splash.point.R:97-115 --------------------------------------------------------
+    const double depth = in.depth;
+    const double SAT = sat * depth * 1000;
+    const double WP = wp * depth * 1000;
+    const double FC = fc * depth * 1000;
+    const double RES = res_frac * depth * 1000;
+    const double Wmax_R = theta_c * depth * 1000;
+    const double lambda = 1 / coef_B;
+    const double bub = bubbling_p;
+    const double Ai = in.resolution * in.resolution;
+    dg.sat = SAT;
+    dg.wp = WP;
+    dg.fc = FC;
+    dg.ksat = ksat;
+    dg.lambda = lambda;
+    dg.depth = depth;
+    dg.bub = bub;
+    dg.res = RES;
+    dg.wmax_r = Wmax_R;
+
+    // ---- snow partition and geometry ---------------------------------------------------------------
+    cc(C_ELEV_K) = in.elev * 0.0004596581;
+    cc(C_LAT_K) = fabs(in.lat) * 0.0110592101;
+    const double asp = in.asp - 180;  // R/splash.point.R:131
+    cc(C_COS_LAT) = cos(in.lat * kpir);
+    cc(C_SIN_LAT) = sin(in.lat * kpir);
+    cc(C_SIN_S) = sin(in.slop * kpir);
+    const double cos_s = cos(in.slop * kpir);
+    cc(C_COS_S) = cos_s;
+    cc(C_COS_A) = cos(asp * kpir);
+    cc(C_SIN_A) = sin(asp * kpir);
+    cc(C_TAN_S) = tan(in.slop * kpir);
+    cc(C_COS2_S) = cos_s * cos_s;
+    // ---- atmosphere: SOLAR.cpp:170,197; EVAP.cpp:331-334 -------------------------------------------
+    const double tau_o = (kc + kd) * (1.0 + (2.67e-5) * in.elev);
+    cc(C_TAU_O) = tau_o;
+    cc(C_TAU_A) = tau_o * 0.1898;
+    cc(C_TAU_B) = (tau_o * (1 - 0.1898));
+    const double ep = (kG * kMa) / (kR * kL);
+    double patm = (1.0 - in.elev * kL / kTo);
+    patm = pow(patm, ep);
+    patm *= kPo;
+    cc(C_PATM) = patm;
+    cc(C_PBAR) = (1.0e-5) * patm;
+    const double pbarf = (1.0e-5) * (double)(float)patm;
+    cc(C_PBARF) = pbarf;
+    cc(C_VISC0) = viscosity_h2o(0.0f, density_at(density_poly(0.0), pbarf));
+    // ---- soil column: SPLASH.cpp:971-1029 ----------------------------------------------------------
+    const double d1000 = depth * 1000.0;
+    const double theta_s = SAT / d1000;
+    const double theta_r = RES / d1000;
+    const double theta_fc = FC / d1000;
+    const double theta_wp = WP / d1000;
+    const double dth = (theta_s - theta_r);
+    const double ilam = (1 / lambda);
+    const double e3 = (3.0 * lambda + 1.0);
+    cc(C_SAT) = SAT;
+    cc(C_RES) = RES;
+    cc(C_DEPTH) = depth;
+    cc(C_D1000) = d1000;
+    cc(C_THS) = theta_s;
+    cc(C_THR) = theta_r;
+    cc(C_DTH) = dth;
+    cc(C_ILAM) = ilam;
+    cc(C_NLAM) = (-1 * lambda);
+    cc(C_E3) = e3;
+    cc(C_BUB) = bub;
+    cc(C_BP10) = bub / 10;
+    const double KG_o = 1000.0 / (997 * kG);
+    const double coeff_A = exp(log(33.0) + (1.0 / lambda) * log(theta_fc));
+    const double Wmax = pow((coeff_A * KG_o / (depth)), (1.0 / ((1 / lambda) + 1.0))) * (depth * 1000.0);
+    cc(C_WMAX) = Wmax;
+    cc(C_WMR) = (Wmax - RES);
+    cc(C_THWMAX) = Wmax / (depth * 1000.0);
+    cc(C_INTPERM) = ksat / kfluidity;
+    cc(C_HF) = ((2 + 3 * lambda) / (1 + 3 * lambda)) * (bub / 2);
+    cc(C_KUEXP) = (3.0 + (2.0 / lambda));
+    // ---- lateral flow invariants: SPLASH.cpp:993, 1291-1303, 1326, 1334-1356 -----------------------
+    const double sid_oct = sqrt(Ai / (2.0 * (1 + sqrt(2.0))));
+    cc(C_SIDOCT) = sid_oct;
+    cc(C_AI) = Ai;
+    cc(C_AU) = in.au;
+    {
+        const double theta_q0 = theta_wp + 0.001;
+        const double psi_q0 = bub / pow((((theta_q0 - theta_r) / dth)), ilam);
+        double wtd_q0 = ((bub - psi_q0) / 1000.0);
+        if (wtd_q0 < 0.0 || isnan(wtd_q0)) {
+            wtd_q0 = 0.0;
+        } else if (wtd_q0 > depth) {
+            wtd_q0 = depth;
+        }
+        cc(C_BRQ0) = (pow((bub / psi_q0), e3) - pow((bub / (psi_q0 + (wtd_q0 * 1000.0))), e3));
+        cc(C_DENKB) = ((SAT - WP) * (Ai / 1000.0));
+    }
+    {
+        const double theta_w = (Wmax) / (depth * 1000.0);
+        const double psi_m = bub / pow((((theta_w - theta_r) / dth)), ilam);
+        double wtd = ((bub - psi_m) / 1000.0);
+        if (wtd < 0.0 || isnan(wtd)) {
+            wtd = 0.01;
+        } else if (wtd > depth) {
+            wtd = depth;
+        }
+        cc(C_ACSW) = (depth - wtd) * in.cellin * sid_oct;
+        cc(C_BRW) = (pow((bub / psi_m), e3) - pow((bub / (psi_m + (wtd * 1000.0))), e3));
+        cc(C_CW) = ((24.0 * in.cellin * sid_oct) / (1.0e6));
+    }
+    lateral_consts(cc, in.cellout);
+    cc(C_WRR) = (Wmax_R - RES);
+    cc(C_TT) = nan("");
+}
+
+}  // namespace splash

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One libsplash_cuda context for the whole session; fails loudly without a GPU."""
+    from rsplash_b200 import build
+    from rsplash_b200._lib import Context
+
+    build.build()
+    c = Context(0)
+    yield c
+    c.close()
