@@ -135,8 +135,9 @@ typedef struct splash_opts {
 typedef struct splash_stats {
     double h2d_ms;          /* host->device copies (sum over tiles, stream time) */
     double setup_ms;        /* cell-setup + snow-threshold kernels */
-    double spinup_ms;       /* spin-up kernels */
-    double main_ms;         /* daily-integration kernel(s) */
+    double spinup_ms;       /* spin-up kernels up to the bulk daily-integration launch */
+    double main_ms;         /* from the bulk daily-integration launch until the tile's last kernel (bulk + straggler tail) */
+    double bulk_ms;         /* the bulk daily-integration kernel alone (CUDA events on its stream) */
     double d2h_ms;          /* device->host copies */
     double total_ms;        /* wall clock of the call */
     int64_t h2d_bytes;

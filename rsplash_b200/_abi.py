@@ -1,7 +1,7 @@
 """ctypes mirror of include/splash_cuda.h (struct layouts, constants, small helpers).
 
-Kept free of any library loading so that both the product binding (rsplash_b200/_lib.py) and the
-test-side oracle loaders (tests/oracle_lib.py) can share the layouts.
+Kept free of any library loading so that the product binding (rsplash_b200/_lib.py) and test-side
+harnesses can share the layouts.
 """
 from __future__ import annotations
 
@@ -94,6 +94,7 @@ class SplashStats(C.Structure):
         ("setup_ms", C.c_double),
         ("spinup_ms", C.c_double),
         ("main_ms", C.c_double),
+        ("bulk_ms", C.c_double),
         ("d2h_ms", C.c_double),
         ("total_ms", C.c_double),
         ("h2d_bytes", C.c_int64),

@@ -699,7 +699,7 @@ void launch_fused(const RunParams& rp, bool monthly, cudaStream_t s) {
 template <typename FT>
 int run_tile_kernels(splash_ctx* ctx, int slot, RunParams rp, const SetupParams& sp, const splash_opts& opts,
                      const double* state_init_host, int64_t c0, int64_t nc_total, int64_t pitch, int64_t* launches,
-                     cudaEvent_t ev_setup_done, cudaEvent_t ev_spin_done) {
+                     cudaEvent_t ev_setup_done, cudaEvent_t ev_spin_done, cudaEvent_t ev_bulk_done) {
     const int nct = rp.n_cells;
     const bool monthly = opts.monthly_out != 0;
     cudaStream_t A = ctx->s_run, B = ctx->s_aux;
@@ -731,6 +731,7 @@ int run_tile_kernels(splash_ctx* ctx, int slot, RunParams rp, const SetupParams&
         rp.bulk_only = 1;
         launch_fused<FT>(rp, monthly, A);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(ev_bulk_done, A));
         *launches += 2;
         CU(cudaEventRecord(ctx->ev_run[slot], A));
         return SPLASH_OK;
@@ -766,6 +767,7 @@ int run_tile_kernels(splash_ctx* ctx, int slot, RunParams rp, const SetupParams&
         bp.bulk_only = 1;
         launch_fused<FT>(bp, monthly, A);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(ev_bulk_done, A));
         ++*launches;
         bulk_launched = true;
         return SPLASH_OK;
@@ -1049,12 +1051,12 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
     // ---- per-tile timing events and final counters ----------------------------------------------------------
     struct TileEv {
         cudaEvent_t c0, c1;          // h2d stream: begin / end of the tile's uploads
-        cudaEvent_t k0, k1, k2, k3;  // run stream: begin, setup done, spin-up done (bulk launch), all kernels done
+        cudaEvent_t k0, k1, k2, kb, k3;  // run stream: begin, setup done, bulk launch, bulk done, all kernels done
         cudaEvent_t o0, o1;          // d2h stream: begin / end of the tile's downloads
     };
     std::vector<TileEv> tev((size_t)n_tiles);
     for (auto& t : tev) {
-        cudaEvent_t* evs[8] = {&t.c0, &t.c1, &t.k0, &t.k1, &t.k2, &t.k3, &t.o0, &t.o1};
+        cudaEvent_t* evs[9] = {&t.c0, &t.c1, &t.k0, &t.k1, &t.k2, &t.kb, &t.k3, &t.o0, &t.o1};
         for (auto* e : evs) CU(cudaEventCreate(e));
     }
     unsigned long long* h_final = nullptr;
@@ -1208,9 +1210,9 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
             }
             int rc;
             if (in->forcing_dtype == SPLASH_F32)
-                rc = run_tile_kernels<float>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2);
+                rc = run_tile_kernels<float>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2, ev.kb);
             else
-                rc = run_tile_kernels<double>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2);
+                rc = run_tile_kernels<double>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2, ev.kb);
             if (rc) return rc;
             CU(cudaEventRecord(ev.k3, ctx->s_run));
             CU(cudaMemcpyAsync(h_final + (size_t)t * NCOUNTERS, ctx->counters[s].p, sizeof(unsigned long long) * NCOUNTERS,
@@ -1250,7 +1252,7 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
         return SPLASH_OK;
     };
     const int rc_all = run_tiles();
-    double t_h2d = 0, t_setup = 0, t_spin = 0, t_main = 0, t_d2h = 0;
+    double t_h2d = 0, t_setup = 0, t_spin = 0, t_main = 0, t_bulk = 0, t_d2h = 0;
     if (rc_all == SPLASH_OK) {
         for (auto& t : tev) {
             float ms = 0;
@@ -1258,6 +1260,7 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
             if (cudaEventElapsedTime(&ms, t.k0, t.k1) == cudaSuccess) t_setup += ms;
             if (cudaEventElapsedTime(&ms, t.k1, t.k2) == cudaSuccess) t_spin += ms;
             if (cudaEventElapsedTime(&ms, t.k2, t.k3) == cudaSuccess) t_main += ms;
+            if (cudaEventElapsedTime(&ms, t.k2, t.kb) == cudaSuccess) t_bulk += ms;
             if (cudaEventElapsedTime(&ms, t.o0, t.o1) == cudaSuccess) t_d2h += ms;
         }
         for (int64_t t = 0; t < n_tiles; ++t) {
@@ -1269,7 +1272,7 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
         cudaDeviceSynchronize();
     }
     for (auto& t : tev) {
-        cudaEvent_t evs[8] = {t.c0, t.c1, t.k0, t.k1, t.k2, t.k3, t.o0, t.o1};
+        cudaEvent_t evs[9] = {t.c0, t.c1, t.k0, t.k1, t.k2, t.kb, t.k3, t.o0, t.o1};
         for (auto e : evs) cudaEventDestroy(e);
     }
     cudaFreeHost(h_final);
@@ -1279,6 +1282,7 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
     ctx->stats.setup_ms = t_setup;
     ctx->stats.spinup_ms = t_spin;  // up to the launch of the bulk daily kernel
     ctx->stats.main_ms = t_main;    // bulk daily kernel with the straggler tail running beside it
+    ctx->stats.bulk_ms = t_bulk;
     ctx->stats.d2h_ms = t_d2h;
     ctx->stats.main_cell_days = nc * nd;
     ctx->stats.kernel_launches = launches;

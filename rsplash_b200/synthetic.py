@@ -1,6 +1,7 @@
 """Seeded synthetic workloads of the shapes BASELINE.json names.
 
-Used by bench.py (torch, on the GPU, for the 5-arcmin global grid) and by the tests (numpy, small).
+Used by bench.py (torch, on the GPU, for the 5-arcmin global grid) and by the tests (numpy, small;
+tests/synthetic.py wraps it into ABI-shaped problems).
 The generator is written once against a tiny array-namespace shim so both backends run the same
 formulas; values are rounded to FP32-representable doubles like the FLT4S rasters the reference
 reads.  Nothing here is part of the model.
@@ -172,21 +173,3 @@ def make_forcing(xp, lat, elev, doy, chunk_days=None):
 
 def daily_dates(first_year: int, n_years: int) -> np.ndarray:
     return np.arange(np.datetime64(f"{first_year}-01-01"), np.datetime64(f"{first_year + n_years}-01-01"))
-
-
-def make_problem(n_cells: int, n_years: int = 2, seed: int = 0, first_year: int = 2001, flat_fraction: float = 0.5,
-                 lat_range=(-55.0, 72.0), au_layers: int = 3):
-    """Small numpy problem in the ABI layout for the tests -> (tests.oracle_lib.GridProblem, dates)."""
-    from tests import oracle_lib as ol
-    from . import _abi
-
-    xp = backend(seed)
-    lat = xp.f32(lat_range[0] + (lat_range[1] - lat_range[0]) * xp.rand(n_cells))
-    cells = make_cells(xp, lat, flat_fraction=flat_fraction)
-    dates = daily_dates(first_year, n_years)
-    year, doy, month = _abi.time_axes(dates)
-    sw, tc, pn = make_forcing(xp, lat, cells["elev"], doy.astype(np.float64))
-    au = np.stack(cells["au"]) if au_layers == 3 else cells["au"][0][None, :]
-    prob = ol.GridProblem(year, doy, month, sw, tc, pn, lat, cells["elev"], cells["slop"], cells["asp"],
-                          cells["resolution"], np.stack(cells["soil"]), au)
-    return prob, dates

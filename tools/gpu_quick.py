@@ -13,7 +13,7 @@ n_cells = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 n_years = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 prob, dates = make_problem(n_cells, n_years, seed=11)
 ctx = api.default_context()
-for rep in range(2):
+for rep in range(int(sys.argv[3]) if len(sys.argv) > 3 else 2):
     t = time.time()
     r = api.splash_grid(prob.sw_in, prob.tc, prob.pn, prob.lat, prob.elev, prob.slop, prob.asp, prob.soil, prob.au,
                         prob.resolution, dates, monthly_out=True, ctx=ctx, return_diag=True)
