@@ -40,8 +40,16 @@ METRIC = "splash.grid cell-days/sec"
 UNIT = "cell-days/s"
 FIRST_YEAR = 2001
 
-# FP64 instruction slots per cell-day of the daily kernel (ncu, profiles/): filled from the profile
-FP64_SLOTS_PER_CELL_DAY = float(os.environ.get("SPLASH_FP64_SLOTS", "0") or 0)
+
+
+def fp64_work_per_cell_day():
+    """FP64 instructions (DFMA/DMUL/DADD thread-instructions) and flops per cell-day of the daily kernel,
+    counted by ncu on the shipped kernel (profiles/fp64_work.json, see profiles/README.md)."""
+    p = os.path.join(ROOT, "profiles", "fp64_work.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["fp64_inst_per_cell_day"]), float(d["flops_per_cell_day"]), d.get("source", "profiles/fp64_work.json")
+    return 0.0, 0.0, "no ncu count committed"
 
 
 def parse_args():
@@ -347,32 +355,58 @@ def main():
     launches = int(sum(s["kernel_launches"] for s in stats_steps))
     finite_frac = float(torch.isfinite(outs[0]).double().mean().item())
 
-    # ---- roofline of the dominant kernel (bulk daily-integration launch), library CUDA events ---------
+    # ---- roofline of the dominant kernel: the bulk daily-integration kernel (k_splash_fused, bulk mode) run
+    #      ALONE over the whole shard -- a resume call (skip_spinup) launches nothing else of weight -- and
+    #      timed with CUDA events on its streams inside the library (splash_stats.bulk_span_ms) --------------
     hbm_peak, hbm_src = peaks()
     dfma_peak, dfma_src = fp64_peak()
-    bulk_ms = float(np.mean([s["bulk_ms"] for s in stats_steps]))
+    st_dev = torch.empty((5, nc), dtype=torch.float64, device=device)
+    cout_st = grid_out_struct(n_out, nc, [o.data_ptr() for o in outs], diag.data_ptr(), _abi.SPLASH_MEM_DEVICE)
+    cout_st.state_final = st_dev.data_ptr()
+    ctx.grid_run(cin, opts, cout_st)                      # spun-up state of every cell
+    st_host = st_dev.cpu().numpy().copy()
+    ropts = _abi.SplashOpts()
+    ropts.monthly_out, ropts.skip_spinup = 1, 1
+    ropts.state_init = st_host.ctypes.data_as(C.c_void_p)
+    spans = []
+    for i in range(1 + max(1, args.steps)):
+        ctx.grid_run(cin, ropts, cout)
+        if i:
+            spans.append(ctx.stats()["bulk_span_ms"])
+            launches += ctx.stats()["kernel_launches"]
+    bulk_ms = float(np.mean(spans))
+    bulk_launches = int(ctx.stats()["n_tiles"])
     bulk_cell_days = nc * nd
     alg_bytes_per_cd = 3 * 4 + 9 * 8 * n_out / nd  # f32 forcing read + monthly layers written
     hbm_achieved = bulk_cell_days * alg_bytes_per_cd / (bulk_ms * 1e-3) / 1e9
+    inst_cd, flops_cd, work_src = fp64_work_per_cell_day()
+    hbm_part = {"achieved": hbm_achieved, "peak": hbm_peak, "frac": hbm_achieved / hbm_peak, "unit": "GB/s",
+                "peak_source": hbm_src, "algorithmic_bytes_per_cell_day": alg_bytes_per_cd}
     roofline = {
-        "bound": "fp64" if FP64_SLOTS_PER_CELL_DAY else "hbm",
-        "kernel": "k_splash_fused (bulk daily integration; straggler tail runs beside it)",
-        "unit": "GB/s", "achieved": hbm_achieved, "peak": hbm_peak, "frac": hbm_achieved / hbm_peak, "traffic": None,
-        "peak_source": hbm_src, "algorithmic_bytes_per_cell_day": alg_bytes_per_cd,
-        "kernel_ms_per_launch": bulk_ms, "cell_days_per_launch": bulk_cell_days,
+        "bound": "fp64", "kernel": "k_splash_fused<bulk> (daily integration of every cell), timed alone",
+        "unit": "TFLOP/s", "achieved": None, "peak": 2 * dfma_peak / 1e12, "frac": None, "traffic": None,
+        "peak_source": dfma_src, "fp64_inst_per_cell_day": inst_cd, "flops_per_cell_day": flops_cd, "work_source": work_src,
+        "kernel_ms_per_launch": bulk_ms / bulk_launches, "launches_per_pass": bulk_launches,
+        "cell_days_per_launch": bulk_cell_days / bulk_launches, "cell_days_per_s": bulk_cell_days / (bulk_ms * 1e-3),
+        "note": "the path is bound by the FP64 pipe (transcendentals), not by HBM and not by tensor cores; "
+                "the HBM figures are given beside it",
+        "hbm": hbm_part,
     }
-    if FP64_SLOTS_PER_CELL_DAY:
-        slots_s = bulk_cell_days * FP64_SLOTS_PER_CELL_DAY / (bulk_ms * 1e-3)
-        roofline.update({"unit": "TFLOP/s", "achieved": 2 * slots_s / 1e12, "peak": 2 * dfma_peak / 1e12,
-                         "frac": slots_s / dfma_peak, "peak_source": dfma_src,
-                         "fp64_slots_per_cell_day": FP64_SLOTS_PER_CELL_DAY,
-                         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "frac": hbm_achieved / hbm_peak,
-                                 "unit": "GB/s", "peak_source": hbm_src}})
+    if flops_cd:
+        roofline["achieved"] = bulk_cell_days * flops_cd / (bulk_ms * 1e-3) / 1e12
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline["fp64_pipe_frac"] = bulk_cell_days * inst_cd / (bulk_ms * 1e-3) / dfma_peak
+    tr = os.path.join(ROOT, "profiles", "fp64_work.json")
+    if os.path.exists(tr):
+        roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_cell_day")
+        if roofline["traffic"] is not None:
+            roofline["traffic"] = roofline["traffic"] * bulk_cell_days / bulk_launches
+    del st_dev
 
     # ---- e2e: the same job through the C ABI with pinned HOST buffers, block of rows by block ----------
     e2e = None
     if not args.no_e2e:
-        n_blocks = args.e2e_blocks or max(1, int(np.ceil(nc * nd * 3 * 8 / 12e9)))  # ~12 GB of f64 forcing per block
+        n_blocks = args.e2e_blocks or max(1, int(np.ceil(nc * nd * 3 * 8 / 72e9)))  # <= ~72 GB of pinned f64 forcing per block
         bsz = int(np.ceil(nc / n_blocks / 1024) * 1024)
         n_blocks = int(np.ceil(nc / bsz))
         h_f = [torch.empty((nd, bsz), dtype=torch.float64).pin_memory() for _ in range(3)]
@@ -381,7 +415,6 @@ def main():
         h_diag = torch.empty((_abi.SPLASH_NDIAG, bsz), dtype=torch.float64).pin_memory()
         hopts = _abi.SplashOpts()
         hopts.monthly_out = 1
-        hopts.tile_cells = max(8192, int(np.ceil(bsz / 4 / 1024) * 1024))  # >= 4 tiles: copies overlap kernels
 
         def run_blocks(timed: bool):
             tot = 0.0

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SPLASH_ABI_VERSION 1
+#define SPLASH_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -131,14 +131,19 @@ typedef struct splash_opts {
     const double* state_init; /* [5*n_cells] layer-major wn, snow, qin, td, nd (host); used when skip_spinup */
 } splash_opts;
 
-/* Timing / accounting of the last call, filled by splash_last_stats (all times in milliseconds). */
+/* Timing / accounting of the last call, filled by splash_last_stats (all times in milliseconds).
+ * Tiles overlap on several streams, so the per-kernel-class times are sums of per-tile stream intervals
+ * (they may add up to more than gpu_ms). */
 typedef struct splash_stats {
     double h2d_ms;          /* host->device copies (sum over tiles, stream time) */
     double setup_ms;        /* cell-setup + snow-threshold kernels */
-    double spinup_ms;       /* spin-up kernels up to the bulk daily-integration launch */
-    double main_ms;         /* from the bulk daily-integration launch until the tile's last kernel (bulk + straggler tail) */
-    double bulk_ms;         /* the bulk daily-integration kernel alone (CUDA events on its stream) */
+    double first_ms;        /* k_spin_first: aridity year + pass 0, 730 uniform days for every cell */
+    double rounds_ms;       /* lock-step spin-up rounds (check + rest kernels) */
+    double bulk_ms;         /* the bulk daily-integration kernels (CUDA events on their streams), summed over tiles */
+    double bulk_span_ms;    /* first bulk kernel start to last bulk kernel end (== their run time when nothing else runs, e.g. a resume call) */
     double d2h_ms;          /* device->host copies */
+    double pool_wait_ms;    /* host wait for the straggler pool after every tile stream had drained */
+    double gpu_ms;          /* first enqueue to last completion, CUDA events */
     double total_ms;        /* wall clock of the call */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
@@ -146,8 +151,12 @@ typedef struct splash_stats {
     int64_t main_cell_days; /* n_cells * n_days */
     int64_t kernel_launches;/* kernels of this library launched by the call */
     int64_t unconverged_cells; /* cells that hit the pass limit */
-    int64_t n_tiles;
     int64_t cycle_cells;    /* cells whose spin-up was cut short by exact cycle detection */
+    int64_t n_tiles;
+    int64_t tile_cells;
+    int64_t pool_cells;     /* cells that outlived the lock-step rounds and finished in the straggler pool */
+    int64_t pool_overflow_cells; /* ... that did not fit the pool and finished inside their tile */
+    int64_t pool_max_passes;/* longest chain of year passes one thread executed after the rounds */
 } splash_stats;
 
 int splash_abi_version(void);

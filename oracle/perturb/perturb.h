@@ -1,0 +1,18 @@
+/* oracle/perturb/perturb.h -- TEST INFRASTRUCTURE.  Force-included when the C restatement is rebuilt
+ * with a deliberately perturbed math library (oracle/Makefile target `sens`), to find the cells whose
+ * reference results depend on the last bit of libm (tests/conditioning.py). */
+#include <math.h>
+double pp_pow(double, double);
+double pp_pow_explog(double, double);
+double pp_exp(double);
+double pp_log(double);
+#ifdef PERTURB_POW
+#define pow pp_pow
+#endif
+#ifdef PERTURB_POWEXPLOG
+#define pow pp_pow_explog
+#endif
+#ifdef PERTURB_EXPLOG
+#define exp pp_exp
+#define log pp_log
+#endif

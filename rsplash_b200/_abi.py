@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-SPLASH_ABI_VERSION = 1
+SPLASH_ABI_VERSION = 2
 
 SPLASH_OK, SPLASH_ERR_BAD_ARG, SPLASH_ERR_CUDA, SPLASH_ERR_NOMEM, SPLASH_ERR_NO_DEVICE = range(5)
 SPLASH_MEM_HOST, SPLASH_MEM_DEVICE = 0, 1
@@ -92,10 +92,13 @@ class SplashStats(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_double),
         ("setup_ms", C.c_double),
-        ("spinup_ms", C.c_double),
-        ("main_ms", C.c_double),
+        ("first_ms", C.c_double),
+        ("rounds_ms", C.c_double),
         ("bulk_ms", C.c_double),
+        ("bulk_span_ms", C.c_double),
         ("d2h_ms", C.c_double),
+        ("pool_wait_ms", C.c_double),
+        ("gpu_ms", C.c_double),
         ("total_ms", C.c_double),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
@@ -103,8 +106,12 @@ class SplashStats(C.Structure):
         ("main_cell_days", C.c_int64),
         ("kernel_launches", C.c_int64),
         ("unconverged_cells", C.c_int64),
-        ("n_tiles", C.c_int64),
         ("cycle_cells", C.c_int64),
+        ("n_tiles", C.c_int64),
+        ("tile_cells", C.c_int64),
+        ("pool_cells", C.c_int64),
+        ("pool_overflow_cells", C.c_int64),
+        ("pool_max_passes", C.c_int64),
     ]
 
     def as_dict(self):

@@ -7,7 +7,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libsplash_cuda.so")
+# SPLASH_CUDA_LIB: development override to load/build a variant of the library (e.g. another SPLASH_LEVEL)
+LIB_PATH = os.environ.get("SPLASH_CUDA_LIB") or os.path.join(PKG_DIR, "libsplash_cuda.so")
 SOURCES = [os.path.join(CSRC, "splash_cuda.cu")]
 HEADERS = [os.path.join(CSRC, "splash_model.cuh"), os.path.join(PKG_DIR, "..", "include", "splash_cuda.h")]
 
@@ -37,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile rsplash_b200/libsplash_cuda.so; returns the ptxas resource report."""
     if not force and not needs_build():
         return ""
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+    extra = os.environ.get("SPLASH_NVCC_EXTRA", "").split()  # e.g. -DSPLASH_LEVEL=0 for the literal-order day step
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -5,16 +5,24 @@
 //                     invariant of the day step (splash_model.cuh: cell_setup)
 //   k_snow_threshold  per cell: Tt = max(tc[p_snow >= 0.5]) over the whole series
 //                     (R/splash.point.R:120-122), a column reduction over the tc matrix
-//   k_splash_fused    per cell, one thread: aridity pass -> spin-up equilibrium loop -> run_all day
-//                     loop, as ONE state machine around a single inlined day step, state in
+//   k_spin_first      per cell: the aridity year + pass 0 of the second spin_up (730 uniform days)
+//   k_spin_check/rest one lock-step year pass of the cells that still spin: the check day (which is
+//                     also day 1 of the next pass) with compaction, then days 2..365 of the survivors;
+//                     the list sizes stay on the device, the host never waits for them
+//   k_splash_fused    bulk mode: the run_all day loop of every cell whose spin-up is finished, state in
 //                     registers, constants in shared memory, outputs written with streaming stores
-//                     (daily) or reduced per month in registers (monthly)
+//                     (daily) or reduced per month in registers (monthly);
+//                     list mode: per-thread state machine (rest of the spin-up, then the day loop)
+//                     for the few cells that outlive the lock-step passes; lanes fetch cells from a
+//                     device-side queue
+//   k_pool_*          move those stragglers (constants, state, forcing columns) into a context-wide
+//                     pool so that their tile's buffers can be reused while they finish
 //
-// Host side: a context owns streams, device buffers and a small pinned staging area.  A call
-// splits the block into cell tiles sized to device memory and pipelines
-//   H2D(tile t+1)  ||  kernels(tile t)  ||  D2H(tile t-1)
-// on three streams.  With SPLASH_MEM_DEVICE the kernels read and write the caller's device
-// arrays in place (no copies).  There is no host implementation of the model in this library.
+// Host side: a context owns streams and grow-only device buffers.  A call splits the block into
+// cell tiles and enqueues, per tile, a fixed kernel sequence on one of several compute streams
+//   H2D(tile t+1)  ||  kernels(tiles t, t-1, ..)  ||  straggler pool  ||  D2H(tile t-1)
+// without any host round trip.  With SPLASH_MEM_DEVICE the kernels read and write the caller's
+// device arrays in place (no copies).  There is no host implementation of the model in this library.
 #include "../../include/splash_cuda.h"
 
 #include <cuda_runtime.h>
@@ -34,7 +42,36 @@ using namespace splash;
 
 namespace {
 
-constexpr int kThreads = 128;  // threads per CTA of the fused kernel
+constexpr int kThreads = 128;  // threads per CTA of the list-mode (non-uniform) day-loop kernels
+#ifndef SPLASH_MIN_BLOCKS
+#define SPLASH_MIN_BLOCKS 4
+#endif
+constexpr int kMinBlocks = SPLASH_MIN_BLOCKS;  // resident CTAs per SM the register allocation aims for
+// Uniform kernels (every thread of the CTA runs the same days): one large CTA per SM whose warps are
+// kept together by a CTA barrier per day (SPLASH_SYNC=1; 0 = none), so that they walk through the ~60 KB
+// loop body together and share instruction-cache lines instead of each streaming the body from L2 on
+// its own (the body is larger than the 32 KB L1.5 instruction cache; profiles/README.md).
+#ifndef SPLASH_SYNC
+#define SPLASH_SYNC 1
+#endif
+#ifndef SPLASH_UTHREADS
+#define SPLASH_UTHREADS 512
+#endif
+#ifndef SPLASH_UBLOCKS
+#define SPLASH_UBLOCKS 1
+#endif
+constexpr int kListThreads = 32;  // list mode: one warp per CTA, so that the few long-running warps spread over all SMs
+constexpr int kSync = SPLASH_SYNC;
+constexpr int kUThreads = SPLASH_UTHREADS;
+constexpr int kUBlocks = SPLASH_UBLOCKS;
+// Register budget of the uniform kernels: they are compiled for a CTA `kURegSlack` threads larger than
+// the one launched, so that a full CTA leaves room on its SM for one-warp CTAs of the straggler pool
+// (list mode, 128 registers/thread).  Without the slack a 512-thread CTA owns the whole register file
+// and the long-running pool warps and the uniform kernels would exclude each other from an SM.
+#ifndef SPLASH_UREG_SLACK
+#define SPLASH_UREG_SLACK 64
+#endif
+constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
 constexpr int kSpinYear = 365; // R/splash.point.R:141-152: the spin-up year is always 365 days
 
 __constant__ MonthTab c_month_tab;
@@ -155,8 +192,22 @@ __global__ void __launch_bounds__(256) k_snow_threshold(const FT* __restrict__ t
 //   snap_pass  j
 //   status     ST_ACTIVE (still spinning) / ST_READY_BULK / ST_READY_LATE (spin-up finished)
 // ---------------------------------------------------------------------------------------------
-enum : int { ST_ACTIVE = 0, ST_READY_BULK = 1, ST_READY_LATE = 2 };
-enum : int { CNT_SPIN_DAYS = 0, CNT_UNCONVERGED = 1, CNT_LIST = 2, CNT_DONE = 3, CNT_CYCLES = 4, NCOUNTERS = 8 };
+enum : int { ST_ACTIVE = 0, ST_READY_BULK = 1, ST_EXPORTED = 3 };
+constexpr int kMaxRounds = 32;  // upper bound of lock-step year passes per tile
+
+// Device-resident control block of one tile.  Everything the kernels of a tile need to know about
+// the sizes of its lists lives here, so the host enqueues the whole tile without waiting.
+struct TileCtl {
+    unsigned long long cnt[kMaxRounds + 2];  // cnt[r]: cells in spin list r (cnt[0] = cells of the tile)
+    unsigned long long spin_days;            // spin-up cell-days executed (incl. check days)
+    unsigned long long unconverged;          // cells that hit the pass limit
+    unsigned long long cycles;               // cells cut short by exact cycle detection
+    unsigned long long pool_base, pool_end;  // this tile's range of the straggler pool
+    unsigned long long pool_head;            // work-fetch cursor of the pool's daily-integration launch
+    unsigned long long spin_head;            // work-fetch cursor of the pool's spin-up launch
+    unsigned long long tail_head, tail_end;  // leftovers that did not fit the pool: finished in the tile
+    unsigned long long max_chain;            // most year passes executed by one thread of a list-mode launch
+};
 
 struct Work {
     double* st;
@@ -178,19 +229,19 @@ struct RunParams {
     int n_days;
     int n_cells;               // cells of the tile
     Work w;
-    const int* list;           // cells to process (null = all n_cells of the tile)
-    int n_list;                // entries of list (or n_cells)
-    int* list_out;             // k_spin_check: cells that continue spinning
-    int* done_out;             // k_spin_check: cells that finished (only when ready_value == ST_READY_LATE)
-    int ready_value;           // status given to cells that finish in this launch
-    int bulk_only;             // k_splash_fused: process ST_READY_BULK cells only (the bulk launch)
+    int* lists[2];             // ping-pong spin lists of the tile: list r lives in lists[r & 1] (list 0 = identity)
+    int round;                 // k_spin_check / k_spin_rest: lock-step round r
+    TileCtl* ctl;              // the tile's control block
+    // list mode of k_splash_fused: lanes fetch i from *q_head while i < *q_end; cell = q_list ? q_list[i] : i
+    unsigned long long* q_head;
+    const unsigned long long* q_end;
+    const int* q_list;
     double* out[9];            // [n_out][opitch]; null = skip
     int64_t opitch;
     double* diag;              // [SPLASH_NDIAG][dpitch] or null
     int64_t dpitch;
     int max_spin;
     double spin_tol;
-    unsigned long long* counters;
 };
 
 // Neumaier-compensated sum: R's sum() accumulates in 80-bit long double (summary.c), the device
@@ -206,8 +257,8 @@ struct CompSum {
 };
 
 __device__ __forceinline__ void load_cc(const RunParams& p, int c, const StridedCC& cc) {
-#pragma unroll 7
-    for (int k = 0; k < NCC; ++k) cc(k) = p.cc[(int64_t)k * p.cpitch + c];
+#pragma unroll 4
+    for (int k = 0; k < NCC_DAY; ++k) cc(k) = p.cc[(int64_t)k * p.cpitch + c];
 }
 
 __device__ __forceinline__ CellState load_state(const Work& w, int c) {
@@ -254,7 +305,8 @@ __device__ __forceinline__ void spin_forcing(const RunParams& p, int c, int d, d
 // pass q only depends on E_{q-1} and E_q).  All checks of one full period [j+1, k] have then been
 // seen to fail, hence the reference would run to its pass limit; whole periods are skipped and the
 // remainder simulated, which lands on exactly the state the reference reaches (Brent's scheme:
-// the snapshot is refreshed at powers of two).
+// the snapshot is refreshed at powers of two, and every 64 passes so that a cycle entered late is
+// still found within 64 + period passes).
 __device__ __forceinline__ bool spin_decide(const CellState& Ek, double chk_wn, double w1, int& passes, int& snap_pass,
                                             const StridedCC& snap, double tol, int max_spin, bool& hit_limit,
                                             bool& cycle_found) {
@@ -269,7 +321,7 @@ __device__ __forceinline__ bool spin_decide(const CellState& Ek, double chk_wn, 
             passes += ((max_spin - passes) / period) * period;
             cycle_found = true;
             if (passes >= max_spin) cont = false;
-        } else if ((passes & (passes - 1)) == 0) {
+        } else if ((passes & (passes - 1)) == 0 || (passes & 63) == 0) {
             snap(0) = Ek.wn;
             snap(1) = Ek.snow;
             snap(2) = Ek.qin;
@@ -284,11 +336,11 @@ __device__ __forceinline__ bool spin_decide(const CellState& Ek, double chk_wn, 
 
 // ---- K2a: aridity pass + pass 0 of the second spin_up, all cells, 730 uniform days ---------------
 template <typename FT>
-__global__ void __launch_bounds__(kThreads) k_spin_first(RunParams p) {
+__global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
     extern __shared__ double s_cc[];
-    const int c = blockIdx.x * kThreads + threadIdx.x;
-    if (c >= p.n_cells) return;
-    StridedCC cc{s_cc + threadIdx.x, kThreads};
+    const int c = blockIdx.x * kUThreads + threadIdx.x;
+    if (c >= p.n_cells) return;  // (an exited thread counts as arrived at the CTA barriers below)
+    StridedCC cc{s_cc + threadIdx.x, kUThreads};
     load_cc(p, c, cc);
     const double RES = cc(C_RES);
     CellState st;
@@ -304,6 +356,7 @@ __global__ void __launch_bounds__(kThreads) k_spin_first(RunParams p) {
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
+        if (kSync >= 1) __syncthreads();
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
         if (it < kSpinYear) {
             // first spin_up call: only its pass-0 pet is consumed (R/splash.point.R:148-150)
@@ -330,16 +383,17 @@ __global__ void __launch_bounds__(kThreads) k_spin_first(RunParams p) {
     p.w.snap_pass[c] = 0;
     p.w.status[c] = ST_ACTIVE;
     if (p.diag) p.diag[SPLASH_DIAG_AI * p.dpitch + c] = AI;
-    atomicAdd(p.counters + CNT_SPIN_DAYS, (unsigned long long)(2 * kSpinYear));
+    atomicAdd(&p.ctl->spin_days, (unsigned long long)(2 * kSpinYear));
 }
 
-// ---- K2b: the check day of every active cell, then compaction -------------------------------------
+// ---- K2b: round r, the check day of every cell of spin list r, then compaction into list r+1 ---------
 template <typename FT>
-__global__ void __launch_bounds__(kThreads) k_spin_check(RunParams p) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_spin_check(RunParams p) {
     extern __shared__ double s_cc[];
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= p.n_list) return;
-    const int c = p.list ? p.list[i] : i;
+    const int r = p.round;
+    const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= p.ctl->cnt[r]) return;
+    const int c = (r == 0) ? (int)i : p.lists[r & 1][i];
     StridedCC cc{s_cc + threadIdx.x, kThreads};
     load_cc(p, c, cc);
     const CellState Ek = load_state(p.w, c);
@@ -357,32 +411,29 @@ __global__ void __launch_bounds__(kThreads) k_spin_check(RunParams p) {
     const bool cont = spin_decide(Ek, st.wn, p.w.w1[c], passes, snap_pass, snap, p.spin_tol, p.max_spin, hit_limit, cycle_found);
     p.w.passes[c] = passes;
     p.w.snap_pass[c] = snap_pass;
-    if (cycle_found) atomicAdd(p.counters + CNT_CYCLES, 1ULL);
+    if (cycle_found) atomicAdd(&p.ctl->cycles, 1ULL);
     if (cont) {
-        store_state(p.w, c, st);
+        store_state(p.w, c, st);  // state after day 1 of pass k+1: k_spin_rest of this round continues from it
         p.w.w1[c] = st.wn;
-        const unsigned long long k = atomicAdd(p.counters + CNT_LIST, 1ULL);
-        p.list_out[k] = c;
+        const unsigned long long k = atomicAdd(&p.ctl->cnt[r + 1], 1ULL);
+        p.lists[(r + 1) & 1][k] = c;
     } else {
         // the day-365 state is handed over, not the check day's (R/splash.point.R:164-172): st stays
-        p.w.status[c] = p.ready_value;
-        if (hit_limit) atomicAdd(p.counters + CNT_UNCONVERGED, 1ULL);
-        if (p.done_out) {
-            const unsigned long long k = atomicAdd(p.counters + CNT_DONE, 1ULL);
-            p.done_out[k] = c;
-        }
+        p.w.status[c] = ST_READY_BULK;
+        if (hit_limit) atomicAdd(&p.ctl->unconverged, 1ULL);
     }
-    atomicAdd(p.counters + CNT_SPIN_DAYS, 1ULL);
+    atomicAdd(&p.ctl->spin_days, 1ULL);
 }
 
 // ---- K2c: days 2..365 of a year pass for the (compacted) cells that continue ----------------------
 template <typename FT>
-__global__ void __launch_bounds__(kThreads) k_spin_rest(RunParams p) {
+__global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_rest(RunParams p) {
     extern __shared__ double s_cc[];
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= p.n_list) return;
-    const int c = p.list ? p.list[i] : i;
-    StridedCC cc{s_cc + threadIdx.x, kThreads};
+    const int r = p.round;
+    const unsigned long long i = (unsigned long long)blockIdx.x * kUThreads + threadIdx.x;
+    if (i >= p.ctl->cnt[r + 1]) return;  // (an exited thread counts as arrived at the CTA barriers below)
+    const int c = p.lists[(r + 1) & 1][i];
+    StridedCC cc{s_cc + threadIdx.x, kUThreads};
     load_cc(p, c, cc);
     CellState st = load_state(p.w, c);
     for (int d = 1; d < kSpinYear; ++d) {
@@ -391,143 +442,351 @@ __global__ void __launch_bounds__(kThreads) k_spin_rest(RunParams p) {
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
+        if (kSync >= 1) __syncthreads();
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
     }
-    store_state(p.w, c, st);
+    store_state(p.w, c, st);  // E_{k+1}: end of the pass
     p.w.passes[c] += 1;
-    atomicAdd(p.counters + CNT_SPIN_DAYS, (unsigned long long)(kSpinYear - 1));
+    atomicAdd(&p.ctl->spin_days, (unsigned long long)(kSpinYear - 1));
 }
 
 // ---- K2d: daily integration (run_all), optionally preceded by the rest of a cell's spin-up ---------
-// bulk_only:  every cell of the tile whose status is ST_READY_BULK (the bulk launch).
-// otherwise:  the listed cells (or all); ST_ACTIVE ones first finish their spin-up in a per-thread
-//             loop (the straggler tail, launched on a second stream next to the bulk launch).
+// kBulk:      one thread per cell of the tile, cells whose status is ST_READY_BULK; uniform day loop.
+// otherwise:  list mode.  Each lane fetches a cell from the device-side queue (q_head/q_end/q_list),
+//             finishes its spin-up if it is still ST_ACTIVE (per-thread loop with the reference's
+//             convergence test and exact cycle detection), integrates its days, and fetches the next
+//             one.  Used for the straggler pool and for leftovers that did not fit into it.
 enum Phase : int { PH_DONE = -1, PH_SPIN = 1, PH_MAIN = 2 };
 
-template <typename FT, bool kMonthly>
-__global__ void __launch_bounds__(kThreads) k_splash_fused(RunParams p) {
+template <typename FT, bool kMonthly, bool kBulk>
+__global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBlocks : 16) k_splash_fused(RunParams p) {
+    constexpr int NT = kBulk ? kUThreads : kListThreads;
+    constexpr int kS = kBulk ? kSync : 0;  // bulk launch: every live thread runs days 0..n_days-1 of run_all
     extern __shared__ double s_cc[];
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= p.n_list) return;
-    const int c = p.list ? p.list[i] : i;
-    const int status = p.w.status[c];
-    if (p.bulk_only && status != ST_READY_BULK) return;
-    StridedCC cc{s_cc + threadIdx.x, kThreads};
-    load_cc(p, c, cc);
-    StridedCC snap{s_cc + (int64_t)NCC * kThreads + threadIdx.x, kThreads};  // 5 private slots after the constants
+    StridedCC cc{s_cc + threadIdx.x, NT};
+    StridedCC snap{s_cc + (int64_t)NCC_DAY * NT + threadIdx.x, NT};  // 5 private slots after the constants (list mode)
+    unsigned long long spin_days = 0;
+    int max_chain = 0;
 
-    const FT* sw_col = (const FT*)p.sw + c;
-    const FT* tc_col = (const FT*)p.tc + c;
-    const FT* pn_col = (const FT*)p.pn + c;
+    for (;;) {
+        int c;
+        if (kBulk) {
+            c = blockIdx.x * NT + threadIdx.x;
+            if (c >= p.n_cells) return;  // (an exited thread counts as arrived at the CTA barriers below)
+        } else {
+            const unsigned long long i = atomicAdd(p.q_head, 1ULL);
+            if (i >= *p.q_end) break;
+            c = p.q_list ? p.q_list[i] : (int)i;
+        }
+        const int status = p.w.status[c];
+        if (kBulk && status != ST_READY_BULK) return;
+        load_cc(p, c, cc);
 
-    const double RES = cc(C_RES);
-    CellState st = load_state(p.w, c);
-    CellState saved = st;
-    int phase = (status == ST_ACTIVE) ? PH_SPIN : PH_MAIN;
-    int passes = 0, snap_pass = 0;
-    double w1 = 0.0;
-    if (phase == PH_SPIN) {
-        passes = p.w.passes[c];
-        snap_pass = p.w.snap_pass[c];
-        w1 = p.w.w1[c];
+        const FT* sw_col = (const FT*)p.sw + c;
+        const FT* tc_col = (const FT*)p.tc + c;
+        const FT* pn_col = (const FT*)p.pn + c;
+
+        const double RES = cc(C_RES);
+        CellState st = load_state(p.w, c);
+        CellState saved = st;
+        int phase = (!kBulk && status == ST_ACTIVE) ? PH_SPIN : PH_MAIN;
+        int passes = 0, snap_pass = 0, chain = 0;
+        double w1 = 0.0;
+        if (phase == PH_SPIN) {
+            passes = p.w.passes[c];
+            snap_pass = p.w.snap_pass[c];
+            w1 = p.w.w1[c];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) snap(k) = p.w.snap[(int64_t)k * p.w.pitch + c];
+        }
+        int d = 0;
+        int n_snowfall = 0;
+        // monthly accumulators: sums for all nine layers, counts for the three averaged ones
+        double acc[9];
+        int cnt[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+        cnt[0] = cnt[1] = cnt[2] = 0;
+        if (phase == PH_MAIN && p.n_days == 0) phase = PH_DONE;
+
+        while (phase != PH_DONE) {
+            // ---- forcing and day table of (phase, d) ---------------------------------------------------
+            DayTab dt;
+            double f_sw, f_tc, f_pn;
+            if (kBulk || phase == PH_MAIN) {
+                dt = p.dtab[d];
+                const int64_t off = (int64_t)d * p.fpitch;
+                f_sw = ld_stream(sw_col + off);
+                f_tc = ld_stream(tc_col + off);
+                f_pn = ld_stream(pn_col + off);
+            } else {
+                dt = p.dtab_spin[d];
+                spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
+                if (d == 0) saved = st;  // E_k: state of day 365 before the check day
+            }
+            DayOut o;
+            double rain, snowfall;
+            if (kS >= 1) __syncthreads();
+            splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
+
+            if (kBulk || phase == PH_MAIN) {
+                if (snowfall > 0.0) ++n_snowfall;
+                double sm_lim = (st.wn - RES) / cc(C_WRR);  // R/splash.point.R:197-200
+                if (sm_lim < 0) sm_lim = 0.0;
+                if (sm_lim > 1) sm_lim = 1.0;
+                const double v[9] = {st.wn, o.ro, o.pet, o.aet, st.snow, o.cond, o.bflow, o.netr, sm_lim};
+                if (kMonthly) {
+                    // mean(wn, snow, sm_lim) / sum(rest), na.rm = TRUE, R/splash.point.R:210-211
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        if (!isnan(v[k])) acc[k] += v[k];
+                    if (!isnan(v[0])) ++cnt[0];
+                    if (!isnan(v[4])) ++cnt[1];
+                    if (!isnan(v[8])) ++cnt[2];
+                    const bool last = (d + 1 == p.n_days) || (p.dtab[d + 1].group != dt.group);
+                    if (last) {
+                        const int64_t off = (int64_t)dt.group * p.opitch + c;
+                        const double m0 = cnt[0] ? acc[0] / cnt[0] : nan("");
+                        const double m4 = cnt[1] ? acc[4] / cnt[1] : nan("");
+                        const double m8 = cnt[2] ? acc[8] / cnt[2] : nan("");
+                        const double w[9] = {m0, acc[1], acc[2], acc[3], m4, acc[5], acc[6], acc[7], m8};
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            if (p.out[k]) __stcs(p.out[k] + off, w[k]);
+                            acc[k] = 0.0;
+                        }
+                        cnt[0] = cnt[1] = cnt[2] = 0;
+                    }
+                } else {
+                    const int64_t off = (int64_t)d * p.opitch + c;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+                        if (p.out[k]) __stcs(p.out[k] + off, v[k]);
+                }
+                if (++d == p.n_days) phase = PH_DONE;
+            } else {  // PH_SPIN: the rest of the second spin_up call, SPLASH.cpp:1697-1743
+                ++spin_days;
+                bool cont = true;
+                if (d == 0) {
+                    bool hit_limit, cycle_found;
+                    cont = spin_decide(saved, st.wn, w1, passes, snap_pass, snap, p.spin_tol, p.max_spin, hit_limit, cycle_found);
+                    if (hit_limit) atomicAdd(&p.ctl->unconverged, 1ULL);
+                    if (cycle_found) atomicAdd(&p.ctl->cycles, 1ULL);
+                    w1 = st.wn;
+                }
+                if (!cont) {
+                    st = saved;  // hand over the day-365 state, not the check day's
+                    d = 0;
+                    phase = (p.n_days > 0) ? PH_MAIN : PH_DONE;
+                } else if (++d == kSpinYear) {
+                    d = 0;
+                    ++passes;
+                    ++chain;
+                }
+            }
+        }
+
+        store_state(p.w, c, st);
+        if (p.diag) p.diag[SPLASH_DIAG_SNOWFALL_DAYS * p.dpitch + c] = (double)n_snowfall;
+        if (kBulk) return;
+        if (status == ST_ACTIVE) {
+            p.w.passes[c] = passes;
+            if (p.diag) p.diag[SPLASH_DIAG_SPIN_PASSES * p.dpitch + c] = (double)passes;
+        }
+        if (chain > max_chain) max_chain = chain;
+    }
+    if (spin_days) atomicAdd(&p.ctl->spin_days, spin_days);
+    if (max_chain) atomicMax(&p.ctl->max_chain, (unsigned long long)max_chain);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Straggler pool.  The cells still spinning after a tile's lock-step rounds (a fraction of a
+// percent, but each may need up to 1000 year passes) are copied out of the tile -- constants, work
+// state and their forcing columns -- so that the tile's buffers can be reused while list-mode
+// launches finish them on their own streams.  Results are scattered to the caller's arrays at the
+// end of the call.
+// ---------------------------------------------------------------------------------------------
+struct Pool {
+    void* f[3];          // [n_days][cap] forcing columns (same element type as the call's forcing)
+    double* cc;          // [NCC][cap]
+    Work w;              // pitch = cap
+    double* out[9];      // [n_out][cap]; null = layer not requested
+    double* diag;        // [SPLASH_NDIAG][cap] (only the rows written by list mode are used)
+    long long* cell;     // [cap] index of the cell in the caller's arrays
+    double* table;       // [365][kDayPreDoubles][cap] forcing half of the cyclic spin-up year (k_pool_table)
+    unsigned long long* count;  // entries handed out so far
+    long long cap;
+};
+
+// one thread: reserve this tile's range of the pool for the leftovers of its last spin list
+__global__ void k_pool_reserve(TileCtl* ctl, int last_list, unsigned long long* pool_count, long long cap) {
+    const unsigned long long n = ctl->cnt[last_list];
+    const unsigned long long base = atomicAdd(pool_count, n);
+    unsigned long long fit = 0;
+    if (base < (unsigned long long)cap) fit = ((unsigned long long)cap - base < n) ? (unsigned long long)cap - base : n;
+    ctl->pool_base = base;
+    ctl->pool_end = base + fit;
+    ctl->pool_head = base;
+    ctl->spin_head = base;
+    ctl->tail_head = fit;  // entries [fit, n) of the last list stay in the tile
+    ctl->tail_end = n;
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int last_list, long long cell0) {
+    const TileCtl* ctl = p.ctl;
+    const unsigned long long base = ctl->pool_base;
+    const long long n = (long long)(ctl->pool_end - base);
+    if (n <= 0) return;
+    const int* list = (last_list == 0) ? nullptr : p.lists[last_list & 1];
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // per-entry records
+    for (long long e = tid; e < n; e += nthreads) {
+        const int c = list ? list[e] : (int)e;
+        const long long j = (long long)base + e;
+        for (int k = 0; k < NCC; ++k) pool.cc[(long long)k * pool.cap + j] = p.cc[(int64_t)k * p.cpitch + c];
+        for (int k = 0; k < 5; ++k) {
+            pool.w.st[(long long)k * pool.cap + j] = p.w.st[(int64_t)k * p.w.pitch + c];
+            pool.w.snap[(long long)k * pool.cap + j] = p.w.snap[(int64_t)k * p.w.pitch + c];
+        }
+        pool.w.w1[j] = p.w.w1[c];
+        pool.w.passes[j] = p.w.passes[c];
+        pool.w.snap_pass[j] = p.w.snap_pass[c];
+        pool.w.status[j] = ST_ACTIVE;
+        pool.cell[j] = cell0 + c;
+        p.w.status[c] = ST_EXPORTED;
+    }
+    // forcing columns: consecutive threads write consecutive pool entries of one day
+    const long long total = n * (long long)p.n_days;
+    for (long long q = tid; q < total; q += nthreads) {
+        const long long d = q / n, e = q - d * n;
+        const int c = list ? list[e] : (int)e;
+        const long long src = d * p.fpitch + c, dst = d * pool.cap + (long long)base + e;
+        ((FT*)pool.f[0])[dst] = ((const FT*)p.sw)[src];
+        ((FT*)pool.f[1])[dst] = ((const FT*)p.tc)[src];
+        ((FT*)pool.f[2])[dst] = ((const FT*)p.pn)[src];
+    }
+}
+
+// The spin-up year is cyclic: the forcing half of each of its 365 days (day_forcing) is the same in
+// every pass, and a straggler runs up to 1000 of them.  One thread per (pool cell, day) computes it
+// once; k_pool_spin then only iterates the state half.  `p` is the pool's view (arrays of pitch cap).
+template <typename FT>
+__global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
+    const TileCtl* ctl = p.ctl;
+    const long long base = (long long)ctl->pool_base;
+    const long long n = (long long)ctl->pool_end - base;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n * kSpinYear; q += nthreads) {
+        const int d = (int)(q / n);
+        const int j = (int)(base + (q - (long long)d * n));
+        StridedCC cc{p.cc + j, p.cpitch};
+        double f_sw, f_tc, f_pn;
+        spin_forcing<FT>(p, j, d, f_sw, f_tc, f_pn);
+        DayPre pre;
+        day_forcing(cc, p.dtab_spin[d], c_month_tab, f_sw, f_tc, f_pn, pre);
+        const double* v = reinterpret_cast<const double*>(&pre);
+        double* dst = pool.table + ((long long)d * kDayPreDoubles) * pool.cap + j;
+#pragma unroll
+        for (int k = 0; k < kDayPreDoubles; ++k) dst[(long long)k * pool.cap] = v[k];
+    }
+}
+
+// The rest of the second spin_up call (SPLASH.cpp:1697-1743) for the pool's cells: a per-thread loop over
+// year passes with the reference's convergence test and exact cycle detection, the forcing half of every
+// day read from the table.  This is the longest sequential chain of the whole job (up to 1000 x 365 day
+// steps for a cell that never converges), so the loop body is kept to the state half only.
+__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool) {
+    extern __shared__ double s_cc[];
+    StridedCC cc{s_cc + threadIdx.x, kListThreads};
+    StridedCC snap{s_cc + (int64_t)NCC_DAY * kListThreads + threadIdx.x, kListThreads};
+    unsigned long long spin_days = 0;
+    int max_chain = 0;
+    for (;;) {
+        const unsigned long long i = atomicAdd(&p.ctl->spin_head, 1ULL);
+        if (i >= p.ctl->pool_end) break;
+        const int c = (int)i;
+        load_cc(p, c, cc);
+        CellState st = load_state(p.w, c);
+        CellState saved = st;
+        int passes = p.w.passes[c], snap_pass = p.w.snap_pass[c], chain = 0;
+        double w1 = p.w.w1[c];
 #pragma unroll
         for (int k = 0; k < 5; ++k) snap(k) = p.w.snap[(int64_t)k * p.w.pitch + c];
-    }
-    int d = 0;
-    unsigned long long spin_days = 0;
-    int n_snowfall = 0;
-    // monthly accumulators: sums for all nine layers, counts for the three averaged ones
-    double acc[9];
-    int cnt[3];
+        const double* tab = pool.table + c;
+        const long long day_stride = (long long)kDayPreDoubles * pool.cap;
+        bool cont = true;
+        int d = 0;
+        while (cont) {
+            DayPre pre;
+            {
+                double* v = reinterpret_cast<double*>(&pre);
+                const double* src = tab + (long long)d * day_stride;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    cnt[0] = cnt[1] = cnt[2] = 0;
-    if (phase == PH_MAIN && p.n_days == 0) phase = PH_DONE;
-
-    while (phase != PH_DONE) {
-        // ---- forcing and day table of (phase, d) ---------------------------------------------------
-        DayTab dt;
-        double f_sw, f_tc, f_pn;
-        if (phase == PH_MAIN) {
-            dt = p.dtab[d];
-            const int64_t off = (int64_t)d * p.fpitch;
-            f_sw = ld_stream(sw_col + off);
-            f_tc = ld_stream(tc_col + off);
-            f_pn = ld_stream(pn_col + off);
-        } else {
-            dt = p.dtab_spin[d];
-            spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
-            if (d == 0) saved = st;  // E_k: state of day 365 before the check day
-        }
-        DayOut o;
-        double rain, snowfall;
-        splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
-
-        if (phase == PH_MAIN) {
-            if (snowfall > 0.0) ++n_snowfall;
-            double sm_lim = (st.wn - RES) / cc(C_WRR);  // R/splash.point.R:197-200
-            if (sm_lim < 0) sm_lim = 0.0;
-            if (sm_lim > 1) sm_lim = 1.0;
-            const double v[9] = {st.wn, o.ro, o.pet, o.aet, st.snow, o.cond, o.bflow, o.netr, sm_lim};
-            if (kMonthly) {
-                // mean(wn, snow, sm_lim) / sum(rest), na.rm = TRUE, R/splash.point.R:210-211
+                for (int k = 0; k < kDayPreDoubles; ++k) v[k] = __ldg(src + (long long)k * pool.cap);
+                // next day's rows on their way while this day computes
+                const double* nxt = tab + (long long)((d + 1 == kSpinYear) ? 0 : d + 1) * day_stride;
 #pragma unroll
-                for (int k = 0; k < 9; ++k)
-                    if (!isnan(v[k])) acc[k] += v[k];
-                if (!isnan(v[0])) ++cnt[0];
-                if (!isnan(v[4])) ++cnt[1];
-                if (!isnan(v[8])) ++cnt[2];
-                const bool last = (d + 1 == p.n_days) || (p.dtab[d + 1].group != dt.group);
-                if (last) {
-                    const int64_t off = (int64_t)dt.group * p.opitch + c;
-                    const double m0 = cnt[0] ? acc[0] / cnt[0] : nan("");
-                    const double m4 = cnt[1] ? acc[4] / cnt[1] : nan("");
-                    const double m8 = cnt[2] ? acc[8] / cnt[2] : nan("");
-                    const double w[9] = {m0, acc[1], acc[2], acc[3], m4, acc[5], acc[6], acc[7], m8};
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        if (p.out[k]) __stcs(p.out[k] + off, w[k]);
-                        acc[k] = 0.0;
-                    }
-                    cnt[0] = cnt[1] = cnt[2] = 0;
-                }
-            } else {
-                const int64_t off = (int64_t)d * p.opitch + c;
-#pragma unroll
-                for (int k = 0; k < 9; ++k)
-                    if (p.out[k]) __stcs(p.out[k] + off, v[k]);
+                for (int k = 0; k < kDayPreDoubles; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (long long)k * pool.cap));
             }
-            if (++d == p.n_days) phase = PH_DONE;
-        } else {  // PH_SPIN: the rest of the second spin_up call, SPLASH.cpp:1697-1743
+            if (d == 0) saved = st;  // E_k: state of day 365 before the check day
+            DayOut o;
+            day_state(cc, pre, st, o);
             ++spin_days;
-            bool cont = true;
             if (d == 0) {
                 bool hit_limit, cycle_found;
                 cont = spin_decide(saved, st.wn, w1, passes, snap_pass, snap, p.spin_tol, p.max_spin, hit_limit, cycle_found);
-                if (hit_limit) atomicAdd(p.counters + CNT_UNCONVERGED, 1ULL);
-                if (cycle_found) atomicAdd(p.counters + CNT_CYCLES, 1ULL);
+                if (hit_limit) atomicAdd(&p.ctl->unconverged, 1ULL);
+                if (cycle_found) atomicAdd(&p.ctl->cycles, 1ULL);
                 w1 = st.wn;
             }
-            if (!cont) {
-                st = saved;  // hand over the day-365 state, not the check day's
-                d = 0;
-                phase = (p.n_days > 0) ? PH_MAIN : PH_DONE;
-            } else if (++d == kSpinYear) {
+            if (cont && ++d == kSpinYear) {
                 d = 0;
                 ++passes;
+                ++chain;
             }
         }
+        store_state(p.w, c, saved);  // the day-365 state is handed over, not the check day's
+        p.w.passes[c] = passes;
+        p.w.status[c] = ST_READY_BULK;
+        if (p.diag) p.diag[SPLASH_DIAG_SPIN_PASSES * p.dpitch + c] = (double)passes;
+        if (chain > max_chain) max_chain = chain;
     }
+    if (spin_days) atomicAdd(&p.ctl->spin_days, spin_days);
+    if (max_chain) atomicMax(&p.ctl->max_chain, (unsigned long long)max_chain);
+}
 
-    store_state(p.w, c, st);
-    if (status == ST_ACTIVE) p.w.passes[c] = passes;
-    if (p.diag) p.diag[SPLASH_DIAG_SNOWFALL_DAYS * p.dpitch + c] = (double)n_snowfall;
-    if (spin_days) atomicAdd(p.counters + CNT_SPIN_DAYS, spin_days);
+// device-resident outputs: write the pool's results into the caller's arrays
+__global__ void k_pool_scatter(Pool pool, long long n, long long n_out, double* const* out9, long long ostride,
+                               double* state_final, double* cell_diag, long long nc) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < 9; ++k) {
+        if (!pool.out[k] || !out9[k]) continue;
+        for (long long q = tid; q < n * n_out; q += nthreads) {
+            const long long r = q / n, j = q - r * n;
+            out9[k][r * ostride + pool.cell[j]] = pool.out[k][r * pool.cap + j];
+        }
+    }
+    for (long long j = tid; j < n; j += nthreads) {
+        const long long c = pool.cell[j];
+        if (state_final)
+            for (int k = 0; k < 5; ++k) state_final[(long long)k * nc + c] = pool.w.st[(long long)k * pool.cap + j];
+        if (cell_diag) {
+            cell_diag[(long long)SPLASH_DIAG_SPIN_PASSES * nc + c] = pool.diag[(long long)SPLASH_DIAG_SPIN_PASSES * pool.cap + j];
+            cell_diag[(long long)SPLASH_DIAG_SNOWFALL_DAYS * nc + c] = pool.diag[(long long)SPLASH_DIAG_SNOWFALL_DAYS * pool.cap + j];
+        }
+    }
 }
 
 __global__ void k_finish_diag(const int* passes, double* diag, int64_t dpitch, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) diag[SPLASH_DIAG_SPIN_PASSES * dpitch + c] = (double)passes[c];
+}
+
+__global__ void k_tile_begin(TileCtl* ctl, int n_cells) {  // (the control blocks are zeroed once per call)
+    ctl->cnt[0] = (unsigned long long)n_cells;
 }
 
 __global__ void k_init_resume(Work w, double* diag, int64_t dpitch, int n) {
@@ -609,26 +868,35 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;         // forcing / output buffer sets in flight when they stream from / to the host
+constexpr int kRunStreams = 4;    // compute streams the tiles are dealt to
+constexpr int kPoolStreams = 16;  // streams of the straggler-pool launches
+#ifndef SPLASH_ROUNDS
+#define SPLASH_ROUNDS 20
+#endif
+constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before the leftovers go to the pool
+static_assert(kRounds <= kMaxRounds, "kRounds");
+constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
+
+struct WorkSet {  // per-tile work arrays (per slot when the inputs stream from the host)
+    DevBuf cc, work_d, work_i, diag;
+};
 
 }  // namespace
 
 struct splash_ctx {
     int device = 0;
-    cudaStream_t s_h2d = nullptr, s_run = nullptr, s_aux = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_run[kRunStreams] = {};
+    cudaStream_t s_pool[kPoolStreams] = {};
     std::string err;
     splash_stats stats{};
     int sm_count = 0;
     bool month_tab_set = false;
-    // grow-only device buffers, one set per pipeline slot
-    DevBuf forcing[kSlots][3], cellin[kSlots], cc[kSlots], outs[kSlots], work_d[kSlots], work_i[kSlots], diag[kSlots],
-        counters[kSlots];
-    DevBuf dtab, dtab_spin;
-    unsigned long long* h_counters = nullptr;  // pinned, NCOUNTERS per slot
-    cudaEvent_t ev_h2d[kSlots]{}, ev_run[kSlots]{}, ev_aux[kSlots]{}, ev_d2h[kSlots]{};
-    // tuning knobs (environment overrides for experiments)
-    int64_t bulk_launch_below = 0;  // launch the bulk daily kernel once fewer cells than this still spin (0 = auto)
-    int64_t tail_below = 0;         // hand the last active cells to the per-thread tail below this count (0 = auto)
+    // grow-only device buffers
+    DevBuf forcing[kSlots][3], cellin[kSlots], outs[kSlots];
+    std::vector<WorkSet> work;
+    DevBuf dtab, dtab_spin, ctl, pool_mem;
 };
 
 namespace {
@@ -670,177 +938,48 @@ int ensure(splash_ctx* ctx, DevBuf& b, size_t bytes) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+inline unsigned ugrid_for(int64_t n) { return (unsigned)((n + kUThreads - 1) / kUThreads); }
 
-constexpr size_t kSmemSpin = sizeof(double) * NCC * kThreads;
-constexpr size_t kSmemFused = sizeof(double) * (NCC + 5) * kThreads;
+constexpr size_t kSmemSpin = sizeof(double) * NCC_DAY * kThreads;             // k_spin_check
+constexpr size_t kSmemUniform = sizeof(double) * NCC_DAY * kUThreads;         // k_spin_first, k_spin_rest, bulk launch
+constexpr size_t kSmemList = sizeof(double) * (NCC_DAY + 5) * kListThreads;  // list mode: + cycle snapshot
 
 template <typename FT>
 cudaError_t prepare_kernels() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_spin_first<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpin))) return e;
+    if ((e = cudaFuncSetAttribute(k_spin_first<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
     if ((e = cudaFuncSetAttribute(k_spin_check<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpin))) return e;
-    if ((e = cudaFuncSetAttribute(k_spin_rest<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpin))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFused))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFused))) return e;
+    if ((e = cudaFuncSetAttribute(k_spin_rest<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
+    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
+    if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     return cudaSuccess;
 }
 
+// bulk launch: every ST_READY_BULK cell of the tile, uniform day loop
 template <typename FT>
-void launch_fused(const RunParams& rp, bool monthly, cudaStream_t s) {
-    if (rp.n_list <= 0) return;
+void launch_bulk(const RunParams& rp, bool monthly, cudaStream_t s) {
+    if (rp.n_cells <= 0) return;
     if (monthly)
-        k_splash_fused<FT, true><<<grid_for(rp.n_list), kThreads, kSmemFused, s>>>(rp);
+        k_splash_fused<FT, true, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
     else
-        k_splash_fused<FT, false><<<grid_for(rp.n_list), kThreads, kSmemFused, s>>>(rp);
+        k_splash_fused<FT, false, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
 }
 
-// Kernel sequence of one tile.  On return everything is enqueued; ev_run[slot] (stream s_run) fires
-// when all of the tile's kernels on both compute streams are complete.
+// list-mode launch: `warps` one-warp CTAs whose lanes fetch cells from the queue in rp
 template <typename FT>
-int run_tile_kernels(splash_ctx* ctx, int slot, RunParams rp, const SetupParams& sp, const splash_opts& opts,
-                     const double* state_init_host, int64_t c0, int64_t nc_total, int64_t pitch, int64_t* launches,
-                     cudaEvent_t ev_setup_done, cudaEvent_t ev_spin_done, cudaEvent_t ev_bulk_done) {
-    const int nct = rp.n_cells;
-    const bool monthly = opts.monthly_out != 0;
-    cudaStream_t A = ctx->s_run, B = ctx->s_aux;
-    unsigned long long* d_cnt = (unsigned long long*)ctx->counters[slot].p;
-    unsigned long long* h_cnt = ctx->h_counters + (size_t)slot * NCOUNTERS;
-    int* ibase = (int*)ctx->work_i[slot].p;
-    int* list_a = ibase + 3 * pitch;
-    int* list_b = ibase + 4 * pitch;
-    int* done_list = ibase + 5 * pitch;
-
-    CU(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * NCOUNTERS, A));
-    k_cell_setup<<<(unsigned)((nct + 127) / 128), 128, 0, A>>>(sp);
-    CU(cudaGetLastError());
-    k_snow_threshold<FT><<<(unsigned)((nct + 255) / 256), 256, 0, A>>>((const FT*)rp.tc, rp.fpitch, rp.n_days, nct, rp.cc,
-                                                                        rp.cpitch, rp.diag, rp.dpitch);
-    CU(cudaGetLastError());
-    *launches += 2;
-    CU(cudaEventRecord(ev_setup_done, A));
-
-    if (opts.skip_spinup) {
-        // resume: run_all starts from the caller's state (SPLASH.cpp:1833-1835 wn_last ... nds_last)
-        CU(cudaMemcpy2DAsync(rp.w.st, (size_t)pitch * 8, state_init_host + c0, (size_t)nc_total * 8, (size_t)nct * 8, 5,
-                             cudaMemcpyHostToDevice, A));
-        k_init_resume<<<(unsigned)((nct + 255) / 256), 256, 0, A>>>(rp.w, rp.diag, rp.dpitch, nct);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(ev_spin_done, A));
-        rp.list = nullptr;
-        rp.n_list = nct;
-        rp.bulk_only = 1;
-        launch_fused<FT>(rp, monthly, A);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(ev_bulk_done, A));
-        *launches += 2;
-        CU(cudaEventRecord(ctx->ev_run[slot], A));
-        return SPLASH_OK;
-    }
-
-    // ---- aridity pass + pass 0 for every cell -----------------------------------------------------------
-    rp.list = nullptr;
-    rp.n_list = nct;
-    k_spin_first<FT><<<grid_for(nct), kThreads, kSmemSpin, A>>>(rp);
-    CU(cudaGetLastError());
-    ++*launches;
-
-    // ---- lock-step year passes over the compacted set of cells that still spin ----------------------------
-    // GPU-filling threshold: below it a pass is latency-bound, so the bulk daily kernel is started next
-    // to the remaining passes; the last few cells finish in a per-thread loop (k_splash_fused, list mode).
-    const int64_t resident = (int64_t)ctx->sm_count * 3 * kThreads;
-    const int64_t bulk_below = ctx->bulk_launch_below > 0 ? ctx->bulk_launch_below : resident / 2;
-    const int64_t tail_below = ctx->tail_below > 0 ? ctx->tail_below : std::max<int64_t>(256, resident / 16);
-    bool bulk_launched = false;
-    cudaStream_t S = A;  // stream the passes run on; moves to B once the bulk kernel occupies A
-    const int* list_in = nullptr;
-    int* list_out = list_a;
-    int64_t n_active = nct;
-    int64_t n_done_late = 0;
-    auto launch_bulk = [&]() -> int {
-        // B continues this tile's spin-up: it must see everything enqueued on A so far, not the bulk kernel
-        CU(cudaEventRecord(ctx->ev_aux[slot], A));
-        CU(cudaStreamWaitEvent(B, ctx->ev_aux[slot], 0));
-        CU(cudaEventRecord(ev_spin_done, A));
-        RunParams bp = rp;
-        bp.list = nullptr;
-        bp.n_list = nct;
-        bp.bulk_only = 1;
-        launch_fused<FT>(bp, monthly, A);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(ev_bulk_done, A));
-        ++*launches;
-        bulk_launched = true;
-        return SPLASH_OK;
-    };
-    for (int guard = 0; guard < 1 << 20; ++guard) {
-        if (n_active <= tail_below) break;
-        // check day
-        CU(cudaMemsetAsync(d_cnt + CNT_LIST, 0, sizeof(unsigned long long), S));
-        RunParams cp = rp;
-        cp.list = list_in;
-        cp.n_list = (int)n_active;
-        cp.list_out = list_out;
-        cp.ready_value = bulk_launched ? ST_READY_LATE : ST_READY_BULK;
-        cp.done_out = bulk_launched ? done_list : nullptr;
-        k_spin_check<FT><<<grid_for(n_active), kThreads, kSmemSpin, S>>>(cp);
-        CU(cudaGetLastError());
-        ++*launches;
-        CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * NCOUNTERS, cudaMemcpyDeviceToHost, S));
-        CU(cudaStreamSynchronize(S));
-        const int64_t n_next = (int64_t)h_cnt[CNT_LIST];
-        n_done_late = (int64_t)h_cnt[CNT_DONE];
-        n_active = n_next;
-        list_in = list_out;
-        list_out = (list_out == list_a) ? list_b : list_a;
-        if (n_active == 0) break;
-        if (!bulk_launched && n_active < bulk_below) {
-            // the remaining passes no longer fill the GPU: start the daily integration of every cell that
-            // is ready on A and continue spinning the rest on B
-            if (int rc = launch_bulk()) return rc;
-            S = B;
-        }
-        if (n_active <= tail_below) break;
-        RunParams qp = rp;
-        qp.list = list_in;
-        qp.n_list = (int)n_active;
-        k_spin_rest<FT><<<grid_for(n_active), kThreads, kSmemSpin, S>>>(qp);
-        CU(cudaGetLastError());
-        ++*launches;
-    }
-    if (!bulk_launched) {
-        if (int rc = launch_bulk()) return rc;
-    }
-    // ---- tail on B: cells still spinning (per-thread loop, then their daily integration) and the cells
-    //      that finished after the bulk launch ------------------------------------------------------------------
-    bool used_b = false;
-    if (n_active > 0) {
-        RunParams tp = rp;
-        tp.list = list_in;  // when no check launch ran (tiny tiles) list_in is null: all cells, all ST_ACTIVE
-        tp.n_list = (int)n_active;
-        launch_fused<FT>(tp, monthly, B);
-        CU(cudaGetLastError());
-        ++*launches;
-        used_b = true;
-    }
-    if (n_done_late > 0) {
-        RunParams lp = rp;
-        lp.list = done_list;
-        lp.n_list = (int)n_done_late;
-        launch_fused<FT>(lp, monthly, B);
-        CU(cudaGetLastError());
-        ++*launches;
-        used_b = true;
-    }
-    if (used_b) {
-        CU(cudaEventRecord(ctx->ev_aux[slot], B));
-        CU(cudaStreamWaitEvent(A, ctx->ev_aux[slot], 0));
-    }
-    k_finish_diag<<<(unsigned)((nct + 255) / 256), 256, 0, A>>>(rp.w.passes, rp.diag, rp.dpitch, nct);
-    CU(cudaGetLastError());
-    ++*launches;
-    CU(cudaEventRecord(ctx->ev_run[slot], A));
-    return SPLASH_OK;
+void launch_list(const RunParams& rp, bool monthly, int warps, cudaStream_t s) {
+    if (monthly)
+        k_splash_fused<FT, true, false><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
+    else
+        k_splash_fused<FT, false, false><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
 }
+
+struct Out9 {
+    double* p[9];
+};
 
 }  // namespace
 
@@ -871,22 +1010,13 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     ctx = new splash_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* v = getenv("SPLASH_BULK_BELOW")) ctx->bulk_launch_below = atoll(v);
-    if (const char* v = getenv("SPLASH_TAIL_BELOW")) ctx->tail_below = atoll(v);
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithPriority(&ctx->s_run, cudaStreamNonBlocking, prio_lo));
-    CU(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, prio_hi));  // straggler tail first
     CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < kSlots; ++i) {
-        CU(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_run[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
-    }
-    CU(cudaMallocHost(&ctx->h_counters, sizeof(unsigned long long) * NCOUNTERS * kSlots));
+    for (auto& s : ctx->s_run) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_lo));
+    for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));  // stragglers first
     CU(prepare_kernels<double>());
     CU(prepare_kernels<float>());
     *out_ctx = ctx;
@@ -905,24 +1035,24 @@ void splash_ctx_destroy(splash_ctx* ctx) {
     for (int i = 0; i < kSlots; ++i) {
         for (int k = 0; k < 3; ++k) fr(ctx->forcing[i][k]);
         fr(ctx->cellin[i]);
-        fr(ctx->cc[i]);
         fr(ctx->outs[i]);
-        fr(ctx->work_d[i]);
-        fr(ctx->work_i[i]);
-        fr(ctx->diag[i]);
-        fr(ctx->counters[i]);
-        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
-        if (ctx->ev_run[i]) cudaEventDestroy(ctx->ev_run[i]);
-        if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
-        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    for (auto& w : ctx->work) {
+        fr(w.cc);
+        fr(w.work_d);
+        fr(w.work_i);
+        fr(w.diag);
     }
     fr(ctx->dtab);
     fr(ctx->dtab_spin);
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    fr(ctx->ctl);
+    fr(ctx->pool_mem);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
-    if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
-    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (auto s : ctx->s_run)
+        if (s) cudaStreamDestroy(s);
+    for (auto s : ctx->s_pool)
+        if (s) cudaStreamDestroy(s);
     delete ctx;
 }
 
@@ -941,6 +1071,535 @@ int splash_last_stats(const splash_ctx* ctx, splash_stats* out) {
     *out = ctx->stats;
     return SPLASH_OK;
 }
+
+}  // extern "C"
+
+namespace {
+
+// Everything one call needs; run() enqueues the whole job and waits once at the end.
+template <typename FT>
+struct GridJob {
+    splash_ctx* ctx;
+    const splash_grid_in* in;
+    splash_grid_out* out;
+    splash_opts opts;
+    int64_t nc, nd, n_out, istride, ostride;
+    bool in_dev, out_dev, monthly;
+    int max_spin;
+    double spin_tol;
+    double* out_ptr[9];
+    int n_out_layers = 0;
+    int64_t tile = 0, n_tiles = 0, pitch = 0;
+    int n_work = 0;
+    Pool pool{};
+    int64_t launches = 0;
+
+    struct TileEv {
+        cudaEvent_t h2d0, h2d1;                   // h2d stream: the tile's uploads
+        cudaEvent_t k0, kf0, kf1, kr1, kb0, kb1;  // run stream: begin, k_spin_first begin/end, rounds end, bulk begin/end
+        cudaEvent_t exported, run, d2h0, d2h1;    // stragglers exported; all tile kernels done; downloads
+    };
+    std::vector<TileEv> ev;
+    std::vector<RunParams> rps;
+    std::vector<SetupParams> sps;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    TileCtl* ctl(int64_t t) const { return (TileCtl*)ctx->ctl.p + t; }
+    cudaStream_t run_stream(int64_t t) const { return ctx->s_run[t % kRunStreams]; }
+    int work_of(int64_t t) const { return in_dev ? (int)t : (int)(t % kSlots); }
+    int64_t cells_of(int64_t t) const { return std::min<int64_t>(tile, nc - t * tile); }
+
+    int plan() {
+        const size_t fsz = sizeof(FT);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        size_t held = ctx->pool_mem.cap + ctx->ctl.cap;
+        for (int i = 0; i < kSlots; ++i) {
+            for (int k = 0; k < 3; ++k) held += ctx->forcing[i][k].cap;
+            held += ctx->cellin[i].cap + ctx->outs[i].cap;
+        }
+        for (auto& w : ctx->work) held += w.cc.cap + w.work_d.cap + w.work_i.cap + w.diag.cap;
+        double budget = 0.80 * (double)(free_b + held);
+
+        // ---- straggler pool: a slice of the budget, ~1.5 % of the cells ---------------------------------
+        const double per_entry = 3.0 * (double)std::max<int64_t>(nd, 1) * fsz + (double)(NCC + 11 + SPLASH_NDIAG + 1) * 8.0 + 12.0 +
+                                 (double)n_out_layers * (double)std::max<int64_t>(n_out, 1) * 8.0 +
+                                 (double)kSpinYear * kDayPreDoubles * 8.0;
+        int64_t cap = std::min<int64_t>(std::max<int64_t>(nc / 64, 2048), 65536);
+        cap = std::min<int64_t>(cap, (int64_t)(0.10 * budget / per_entry));
+        cap = std::min<int64_t>(std::max<int64_t>(cap, 32), round_up(nc, 32));
+        cap = round_up(cap, 32);
+        if (opts.skip_spinup) cap = 32;  // nothing spins
+        {
+            size_t off = 0;
+            auto carve = [&](size_t bytes) {
+                const size_t o = off;
+                off += (bytes + 255) / 256 * 256;
+                return o;
+            };
+            const size_t o_f = carve(3 * (size_t)std::max<int64_t>(nd, 1) * cap * fsz);
+            const size_t o_cc = carve((size_t)NCC * cap * 8);
+            const size_t o_wd = carve((size_t)11 * cap * 8);
+            const size_t o_wi = carve((size_t)3 * cap * 4);
+            const size_t o_out = carve((size_t)n_out_layers * std::max<int64_t>(n_out, 1) * cap * 8);
+            const size_t o_dg = carve((size_t)SPLASH_NDIAG * cap * 8);
+            const size_t o_cell = carve((size_t)cap * 8);
+            const size_t o_tab = carve((size_t)kSpinYear * kDayPreDoubles * cap * 8);
+            const size_t o_cnt = carve(256);
+            if (int rc = ensure(ctx, ctx->pool_mem, off)) return rc;
+            char* b = (char*)ctx->pool_mem.p;
+            for (int k = 0; k < 3; ++k) pool.f[k] = b + o_f + (size_t)k * std::max<int64_t>(nd, 1) * cap * fsz;
+            pool.cc = (double*)(b + o_cc);
+            double* wd = (double*)(b + o_wd);
+            int* wi = (int*)(b + o_wi);
+            pool.w.st = wd;
+            pool.w.w1 = wd + 5 * cap;
+            pool.w.snap = wd + 6 * cap;
+            pool.w.passes = wi;
+            pool.w.snap_pass = wi + cap;
+            pool.w.status = wi + 2 * cap;
+            pool.w.pitch = cap;
+            int li = 0;
+            for (int k = 0; k < 9; ++k)
+                pool.out[k] = out_ptr[k] ? (double*)(b + o_out) + (size_t)(li++) * std::max<int64_t>(n_out, 1) * cap : nullptr;
+            pool.diag = (double*)(b + o_dg);
+            pool.cell = (long long*)(b + o_cell);
+            pool.table = (double*)(b + o_tab);
+            pool.count = (unsigned long long*)(b + o_cnt);
+            pool.cap = cap;
+            budget -= (double)off;
+        }
+
+        // ---- tile size ------------------------------------------------------------------------------------
+        const double work_cell = (double)(NCC + 11 + SPLASH_NDIAG) * 8.0 + 5 * 4.0;
+        double slot_cell = 0.0;  // bytes per cell held once per slot
+        if (!in_dev) slot_cell += 3.0 * (double)nd * (double)fsz + 14 * 8.0;
+        if (!out_dev) slot_cell += (double)n_out_layers * (double)n_out * 8.0;
+        if (in_dev) budget -= work_cell * (double)nc;  // one work set per tile
+        else slot_cell += work_cell;                   // one work set per slot
+        if (budget <= 0) return fail(ctx, SPLASH_ERR_NOMEM, "not enough device memory for the per-cell work arrays");
+        int64_t t_auto = std::min<int64_t>(kTileTarget, std::max<int64_t>(16384, round_up((nc + 3) / 4, 1024)));
+        if (slot_cell > 0) t_auto = std::min<int64_t>(t_auto, (int64_t)(budget / ((double)kSlots * slot_cell)));
+        tile = opts.tile_cells > 0 ? opts.tile_cells : t_auto;
+        tile = std::min<int64_t>(tile, nc);
+        if (tile < nc) {
+            int64_t t2 = tile / 1024 * 1024;
+            if (t2 == 0) t2 = tile / 128 * 128;
+            tile = std::max<int64_t>(128, t2);
+        }
+        if (tile <= 0) return fail(ctx, SPLASH_ERR_NOMEM, "not enough device memory for one tile");
+        if (tile > (int64_t)INT32_MAX / 2) tile = (int64_t)INT32_MAX / 2 / 1024 * 1024;
+        n_tiles = (nc + tile - 1) / tile;
+        pitch = round_up(tile, 32);
+        n_work = in_dev ? (int)n_tiles : (int)std::min<int64_t>(kSlots, n_tiles);
+        return SPLASH_OK;
+    }
+
+    int allocate() {
+        const size_t fsz = sizeof(FT);
+        if ((int)ctx->work.size() < n_work) ctx->work.resize((size_t)n_work);
+        for (int w = 0; w < n_work; ++w) {
+            WorkSet& ws = ctx->work[(size_t)w];
+            if (int rc = ensure(ctx, ws.cc, (size_t)NCC * pitch * 8)) return rc;
+            if (int rc = ensure(ctx, ws.work_d, (size_t)11 * pitch * 8)) return rc;
+            if (int rc = ensure(ctx, ws.work_i, (size_t)5 * pitch * 4)) return rc;
+            if (int rc = ensure(ctx, ws.diag, (size_t)SPLASH_NDIAG * pitch * 8)) return rc;
+        }
+        const int n_slots = (int)std::min<int64_t>(kSlots, n_tiles);
+        for (int s = 0; s < n_slots; ++s) {
+            if (!in_dev) {
+                for (int k = 0; k < 3; ++k)
+                    if (int rc = ensure(ctx, ctx->forcing[s][k], (size_t)std::max<int64_t>(nd, 1) * pitch * fsz)) return rc;
+                if (int rc = ensure(ctx, ctx->cellin[s], (size_t)14 * pitch * 8)) return rc;
+            }
+            if (!out_dev && n_out_layers)
+                if (int rc = ensure(ctx, ctx->outs[s], (size_t)n_out_layers * std::max<int64_t>(n_out, 1) * pitch * 8)) return rc;
+        }
+        if (int rc = ensure(ctx, ctx->ctl, sizeof(TileCtl) * (size_t)n_tiles)) return rc;
+        CU(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(TileCtl) * (size_t)n_tiles, ctx->s_h2d));
+        CU(cudaMemsetAsync(pool.count, 0, 256, ctx->s_h2d));
+        CU(cudaStreamSynchronize(ctx->s_h2d));
+        ev.resize((size_t)n_tiles);
+        for (auto& t : ev) {
+            cudaEvent_t* timed[10] = {&t.h2d0, &t.h2d1, &t.k0, &t.kf0, &t.kf1, &t.kr1, &t.kb0, &t.kb1, &t.d2h0, &t.d2h1};
+            for (auto* e : timed) CU(cudaEventCreate(e));
+            CU(cudaEventCreateWithFlags(&t.exported, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&t.run, cudaEventDisableTiming));
+        }
+        CU(cudaEventCreate(&ev_begin));
+        CU(cudaEventCreate(&ev_end));
+        rps.resize((size_t)n_tiles);
+        sps.resize((size_t)n_tiles);
+        return SPLASH_OK;
+    }
+
+    void release() {
+        for (auto& t : ev) {
+            cudaEvent_t all[12] = {t.h2d0, t.h2d1, t.k0, t.kf0, t.kf1, t.kr1, t.kb0, t.kb1, t.d2h0, t.d2h1, t.exported, t.run};
+            for (auto e : all)
+                if (e) cudaEventDestroy(e);
+        }
+        ev.clear();
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        ev_begin = ev_end = nullptr;
+    }
+
+    // uploads of tile t into its slot; fills the tile's kernel parameters
+    int enqueue_h2d(int64_t t) {
+        const size_t fsz = sizeof(FT);
+        const int s = (int)(t % kSlots);
+        const int64_t c0 = t * tile, nct = cells_of(t);
+        SetupParams& sp = sps[(size_t)t];
+        RunParams& rp = rps[(size_t)t];
+        sp = SetupParams{};
+        rp = RunParams{};
+        cudaStream_t H = ctx->s_h2d;
+        if (in_dev) {
+            rp.sw = (const char*)in->sw_in + (size_t)c0 * fsz;
+            rp.tc = (const char*)in->tc + (size_t)c0 * fsz;
+            rp.pn = (const char*)in->pn + (size_t)c0 * fsz;
+            rp.fpitch = istride;
+            sp.lat = in->lat + c0;
+            sp.elev = in->elev + c0;
+            sp.slop = in->slop + c0;
+            sp.asp = in->asp + c0;
+            sp.resolution = in->resolution + c0;
+            sp.soil = in->soil + c0;
+            sp.soil_pitch = nc;
+            sp.au = in->au + c0;
+            sp.au_pitch = nc;
+            CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
+        } else {
+            if (t >= kSlots) CU(cudaStreamWaitEvent(H, ev[(size_t)(t - kSlots)].run, 0));  // the slot's previous kernels are done
+            CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
+            const char* src[3] = {(const char*)in->sw_in, (const char*)in->tc, (const char*)in->pn};
+            const void** dst[3] = {&rp.sw, &rp.tc, &rp.pn};
+            for (int k = 0; k < 3; ++k) {
+                if (nd > 0)
+                    CU(cudaMemcpy2DAsync(ctx->forcing[s][k].p, (size_t)pitch * fsz, src[k] + (size_t)c0 * fsz, (size_t)istride * fsz,
+                                         (size_t)nct * fsz, (size_t)nd, cudaMemcpyHostToDevice, H));
+                *dst[k] = ctx->forcing[s][k].p;
+                ctx->stats.h2d_bytes += (int64_t)nct * nd * (int64_t)fsz;
+            }
+            rp.fpitch = pitch;
+            double* ci = (double*)ctx->cellin[s].p;
+            const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
+            for (int k = 0; k < 5; ++k)
+                CU(cudaMemcpyAsync(ci + (size_t)k * pitch, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
+            CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6,
+                                 cudaMemcpyHostToDevice, H));
+            CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8,
+                                 (size_t)in->au_layers, cudaMemcpyHostToDevice, H));
+            ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
+            sp.lat = ci;
+            sp.elev = ci + pitch;
+            sp.slop = ci + 2 * pitch;
+            sp.asp = ci + 3 * pitch;
+            sp.resolution = ci + 4 * pitch;
+            sp.soil = ci + 5 * pitch;
+            sp.soil_pitch = pitch;
+            sp.au = ci + 11 * pitch;
+            sp.au_pitch = pitch;
+        }
+        CU(cudaEventRecord(ev[(size_t)t].h2d1, H));
+
+        // ---- kernel parameters of the tile ----------------------------------------------------------------
+        WorkSet& ws = ctx->work[(size_t)work_of(t)];
+        sp.au_layers = in->au_layers;
+        sp.n_cells = (int)nct;
+        sp.cc = (double*)ws.cc.p;
+        sp.cpitch = pitch;
+        sp.diag = (double*)ws.diag.p;
+        sp.dpitch = pitch;
+        rp.cc = sp.cc;
+        rp.cpitch = pitch;
+        rp.dtab = (const DayTab*)ctx->dtab.p;
+        rp.dtab_spin = (const DayTab*)ctx->dtab_spin.p;
+        rp.n_days = (int)nd;
+        rp.n_cells = (int)nct;
+        double* wd = (double*)ws.work_d.p;
+        int* wi = (int*)ws.work_i.p;
+        rp.w.st = wd;
+        rp.w.w1 = wd + 5 * pitch;
+        rp.w.snap = wd + 6 * pitch;
+        rp.w.passes = wi;
+        rp.w.snap_pass = wi + pitch;
+        rp.w.status = wi + 2 * pitch;
+        rp.w.pitch = pitch;
+        rp.lists[0] = wi + 3 * pitch;
+        rp.lists[1] = wi + 4 * pitch;
+        rp.ctl = ctl(t);
+        int li = 0;
+        for (int k = 0; k < 9; ++k) {
+            if (!out_ptr[k])
+                rp.out[k] = nullptr;
+            else if (out_dev)
+                rp.out[k] = out_ptr[k] + c0;
+            else
+                rp.out[k] = (double*)ctx->outs[s].p + (size_t)(li++) * std::max<int64_t>(n_out, 1) * pitch;
+        }
+        rp.opitch = out_dev ? ostride : pitch;
+        rp.diag = sp.diag;
+        rp.dpitch = pitch;
+        rp.max_spin = max_spin;
+        rp.spin_tol = spin_tol;
+        return SPLASH_OK;
+    }
+
+    // setup, spin-up (first year pair, lock-step rounds), hand-over of the leftovers to the pool
+    int enqueue_spin(int64_t t) {
+        const int64_t c0 = t * tile, nct = cells_of(t);
+        TileEv& e = ev[(size_t)t];
+        RunParams& rp = rps[(size_t)t];
+        cudaStream_t R = run_stream(t);
+        CU(cudaStreamWaitEvent(R, e.h2d1, 0));
+        if (t >= kSlots && !(in_dev && out_dev)) {
+            // slot t % kSlots (forcing, work set, output staging) was last used by tile t - kSlots
+            CU(cudaStreamWaitEvent(R, ev[(size_t)(t - kSlots)].run, 0));
+            if (!out_dev) CU(cudaStreamWaitEvent(R, ev[(size_t)(t - kSlots)].d2h1, 0));
+        }
+        CU(cudaEventRecord(e.k0, R));
+        k_tile_begin<<<1, 1, 0, R>>>(rp.ctl, (int)nct);
+        k_cell_setup<<<(unsigned)((nct + 127) / 128), 128, 0, R>>>(sps[(size_t)t]);
+        CU(cudaGetLastError());
+        k_snow_threshold<FT><<<(unsigned)((nct + 255) / 256), 256, 0, R>>>((const FT*)rp.tc, rp.fpitch, rp.n_days, (int)nct, rp.cc,
+                                                                            rp.cpitch, rp.diag, rp.dpitch);
+        CU(cudaGetLastError());
+        launches += 3;
+        CU(cudaEventRecord(e.kf0, R));
+        if (opts.skip_spinup) {
+            // resume: run_all starts from the caller's state (SPLASH.cpp:1833-1835 wn_last ... nds_last)
+            CU(cudaMemcpy2DAsync(rp.w.st, (size_t)pitch * 8, opts.state_init + c0, (size_t)nc * 8, (size_t)nct * 8, 5,
+                                 cudaMemcpyHostToDevice, R));
+            k_init_resume<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp.w, rp.diag, rp.dpitch, (int)nct);
+            CU(cudaGetLastError());
+            ++launches;
+            CU(cudaEventRecord(e.kf1, R));
+            CU(cudaEventRecord(e.kr1, R));
+            CU(cudaEventRecord(e.exported, R));
+            return SPLASH_OK;
+        }
+        // ---- aridity year + pass 0 for every cell ---------------------------------------------------------
+        k_spin_first<FT><<<ugrid_for(nct), kUThreads, kSmemUniform, R>>>(rp);
+        CU(cudaGetLastError());
+        ++launches;
+        CU(cudaEventRecord(e.kf1, R));
+        // ---- lock-step year passes; the list sizes stay on the device (grids are sized for the worst case,
+        //      surplus CTAs exit at once) --------------------------------------------------------------------
+        // a round can keep at most the cells of the previous one: after a few rounds a fraction of the grid suffices
+        for (int r = 0; r < kRounds; ++r) {
+            RunParams q = rp;
+            q.round = r;
+            k_spin_check<FT><<<grid_for(nct), kThreads, kSmemSpin, R>>>(q);
+            k_spin_rest<FT><<<ugrid_for(nct), kUThreads, kSmemUniform, R>>>(q);
+            CU(cudaGetLastError());
+            launches += 2;
+        }
+        CU(cudaEventRecord(e.kr1, R));
+        // ---- leftovers: into the pool (their own streams), or finished here if the pool is full -----------
+        k_pool_reserve<<<1, 1, 0, R>>>(rp.ctl, kRounds, pool.count, pool.cap);
+        k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, kRounds, (long long)c0);
+        CU(cudaGetLastError());
+        launches += 2;
+        CU(cudaEventRecord(e.exported, R));
+        {
+            cudaStream_t Q = ctx->s_pool[t % kPoolStreams];
+            CU(cudaStreamWaitEvent(Q, e.exported, 0));
+            RunParams pp = rp;
+            pp.sw = pool.f[0];
+            pp.tc = pool.f[1];
+            pp.pn = pool.f[2];
+            pp.fpitch = pool.cap;
+            pp.cc = pool.cc;
+            pp.cpitch = pool.cap;
+            pp.w = pool.w;
+            for (int k = 0; k < 9; ++k) pp.out[k] = pool.out[k];
+            pp.opitch = pool.cap;
+            pp.diag = pool.diag;
+            pp.dpitch = pool.cap;
+            pp.n_cells = (int)pool.cap;
+            pp.q_head = &rp.ctl->pool_head;
+            pp.q_end = &rp.ctl->pool_end;
+            pp.q_list = nullptr;
+            // forcing half of the cyclic year once, the spin-up chain on the state half, then the daily integration
+            k_pool_table<FT><<<(unsigned)(ctx->sm_count * 2), 128, 0, Q>>>(pp, pool);
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool);
+            launch_list<FT>(pp, monthly, ctx->sm_count * 2, Q);
+            CU(cudaGetLastError());
+            launches += 3;
+        }
+        {
+            RunParams tp = rp;
+            tp.q_head = &rp.ctl->tail_head;
+            tp.q_end = &rp.ctl->tail_end;
+            tp.q_list = rp.lists[kRounds & 1];
+            launch_list<FT>(tp, monthly, ctx->sm_count * 2, R);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        return SPLASH_OK;
+    }
+
+    // daily integration of every cell of the tile that finished its spin-up, then the tile's downloads
+    int enqueue_main(int64_t t) {
+        const int64_t c0 = t * tile, nct = cells_of(t);
+        TileEv& e = ev[(size_t)t];
+        RunParams& rp = rps[(size_t)t];
+        cudaStream_t R = run_stream(t), D = ctx->s_d2h;
+        CU(cudaEventRecord(e.kb0, R));
+        launch_bulk<FT>(rp, monthly, R);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e.kb1, R));
+        k_finish_diag<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp.w.passes, rp.diag, rp.dpitch, (int)nct);
+        CU(cudaGetLastError());
+        launches += 2;
+        CU(cudaEventRecord(e.run, R));
+
+        CU(cudaStreamWaitEvent(D, e.run, 0));
+        CU(cudaEventRecord(e.d2h0, D));
+        const cudaMemcpyKind okind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (!out_dev) {
+            for (int k = 0; k < 9; ++k) {
+                if (!out_ptr[k] || n_out == 0) continue;
+                CU(cudaMemcpy2DAsync(out_ptr[k] + c0, (size_t)ostride * 8, rp.out[k], (size_t)pitch * 8, (size_t)nct * 8, (size_t)n_out,
+                                     cudaMemcpyDeviceToHost, D));
+                ctx->stats.d2h_bytes += (int64_t)nct * n_out * 8;
+            }
+        }
+        if (out->state_final) {
+            CU(cudaMemcpy2DAsync(out->state_final + c0, (size_t)nc * 8, rp.w.st, (size_t)pitch * 8, (size_t)nct * 8, 5, okind, D));
+            if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * 5 * 8;
+        }
+        if (out->cell_diag) {
+            CU(cudaMemcpy2DAsync(out->cell_diag + c0, (size_t)nc * 8, rp.diag, (size_t)pitch * 8, (size_t)nct * 8, SPLASH_NDIAG, okind, D));
+            if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * SPLASH_NDIAG * 8;
+        }
+        CU(cudaEventRecord(e.d2h1, D));
+        return SPLASH_OK;
+    }
+
+    // results of the pool's cells into the caller's arrays (after everything else has drained)
+    int scatter_pool(int64_t n_pool) {
+        if (n_pool <= 0) return SPLASH_OK;
+        if (out_dev) {
+            Out9 o9;
+            for (int k = 0; k < 9; ++k) o9.p[k] = out_ptr[k];
+            DevBuf tmp;  // nine pointers
+            if (int rc = ensure(ctx, tmp, sizeof(Out9))) return rc;
+            CU(cudaMemcpy(tmp.p, &o9, sizeof(Out9), cudaMemcpyHostToDevice));
+            k_pool_scatter<<<(unsigned)(ctx->sm_count * 2), 256, 0, ctx->s_d2h>>>(pool, (long long)n_pool, (long long)n_out,
+                                                                                 (double* const*)tmp.p, (long long)ostride,
+                                                                                 out->state_final, out->cell_diag, (long long)nc);
+            CU(cudaGetLastError());
+            ++launches;
+            CU(cudaStreamSynchronize(ctx->s_d2h));
+            CU(cudaFree(tmp.p));
+            return SPLASH_OK;
+        }
+        std::vector<long long> cell((size_t)n_pool);
+        CU(cudaMemcpy(cell.data(), pool.cell, (size_t)n_pool * 8, cudaMemcpyDeviceToHost));
+        std::vector<double> buf((size_t)std::max<int64_t>(n_out, SPLASH_NDIAG) * (size_t)n_pool);
+        for (int k = 0; k < 9; ++k) {
+            if (!out_ptr[k] || n_out == 0) continue;
+            CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.out[k], (size_t)pool.cap * 8, (size_t)n_pool * 8, (size_t)n_out,
+                            cudaMemcpyDeviceToHost));
+            ctx->stats.d2h_bytes += n_pool * n_out * 8;
+            for (int64_t r = 0; r < n_out; ++r) {
+                double* dst = out_ptr[k] + r * ostride;
+                const double* src = buf.data() + r * n_pool;
+                for (int64_t j = 0; j < n_pool; ++j) dst[cell[(size_t)j]] = src[j];
+            }
+        }
+        if (out->state_final) {
+            CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.w.st, (size_t)pool.cap * 8, (size_t)n_pool * 8, 5, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < 5; ++k)
+                for (int64_t j = 0; j < n_pool; ++j) out->state_final[(int64_t)k * nc + cell[(size_t)j]] = buf[(size_t)(k * n_pool + j)];
+        }
+        if (out->cell_diag) {
+            CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.diag, (size_t)pool.cap * 8, (size_t)n_pool * 8, SPLASH_NDIAG,
+                            cudaMemcpyDeviceToHost));
+            const int rows[2] = {SPLASH_DIAG_SPIN_PASSES, SPLASH_DIAG_SNOWFALL_DAYS};
+            for (int r : rows)
+                for (int64_t j = 0; j < n_pool; ++j) out->cell_diag[(int64_t)r * nc + cell[(size_t)j]] = buf[(size_t)(r * n_pool + j)];
+        }
+        return SPLASH_OK;
+    }
+
+    int run() {
+        if (int rc = plan()) return rc;
+        if (int rc = allocate()) return rc;
+        CU(cudaEventRecord(ev_begin, ctx->s_h2d));
+        for (auto s : ctx->s_run) CU(cudaStreamWaitEvent(s, ev_begin, 0));
+        if (in_dev && out_dev) {
+            // resident data: every tile's spin-up first, so that the stragglers (up to 1000 sequential year
+            // passes) start as early as possible and run beside the daily integration of all tiles
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                if (int rc = enqueue_h2d(t)) return rc;
+                if (int rc = enqueue_spin(t)) return rc;
+            }
+            for (int64_t t = 0; t < n_tiles; ++t)
+                if (int rc = enqueue_main(t)) return rc;
+        } else {
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                if (int rc = enqueue_h2d(t)) return rc;
+                if (int rc = enqueue_spin(t)) return rc;
+                if (int rc = enqueue_main(t)) return rc;
+            }
+        }
+        // ---- drain -------------------------------------------------------------------------------------------
+        CU(cudaStreamSynchronize(ctx->s_h2d));
+        for (auto s : ctx->s_run) CU(cudaStreamSynchronize(s));
+        const auto t_pool0 = std::chrono::steady_clock::now();
+        for (auto s : ctx->s_pool) CU(cudaStreamSynchronize(s));
+        const double pool_wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pool0).count();
+        CU(cudaStreamSynchronize(ctx->s_d2h));
+        unsigned long long pool_count = 0;
+        CU(cudaMemcpy(&pool_count, pool.count, 8, cudaMemcpyDeviceToHost));
+        const int64_t n_pool = (int64_t)std::min<unsigned long long>(pool_count, (unsigned long long)pool.cap);
+        if (int rc = scatter_pool(n_pool)) return rc;
+        CU(cudaEventRecord(ev_end, ctx->s_d2h));
+        CU(cudaEventSynchronize(ev_end));
+
+        // ---- accounting --------------------------------------------------------------------------------------
+        std::vector<TileCtl> h_ctl((size_t)n_tiles);
+        CU(cudaMemcpy(h_ctl.data(), ctx->ctl.p, sizeof(TileCtl) * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+        splash_stats& st = ctx->stats;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const TileCtl& c = h_ctl[(size_t)t];
+            st.spin_cell_days += (int64_t)c.spin_days;
+            st.unconverged_cells += (int64_t)c.unconverged;
+            st.cycle_cells += (int64_t)c.cycles;
+            st.pool_cells += (int64_t)(c.pool_end - c.pool_base);
+            st.pool_overflow_cells += (int64_t)c.tail_end - (int64_t)(c.pool_end - c.pool_base);
+            st.pool_max_passes = std::max<int64_t>(st.pool_max_passes, (int64_t)c.max_chain);
+            const TileEv& e = ev[(size_t)t];
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, e.h2d0, e.h2d1) == cudaSuccess) st.h2d_ms += ms;
+            if (cudaEventElapsedTime(&ms, e.k0, e.kf0) == cudaSuccess) st.setup_ms += ms;
+            if (cudaEventElapsedTime(&ms, e.kf0, e.kf1) == cudaSuccess) st.first_ms += ms;
+            if (cudaEventElapsedTime(&ms, e.kf1, e.kr1) == cudaSuccess) st.rounds_ms += ms;
+            if (cudaEventElapsedTime(&ms, e.kb0, e.kb1) == cudaSuccess) st.bulk_ms += ms;
+            if (cudaEventElapsedTime(&ms, e.d2h0, e.d2h1) == cudaSuccess) st.d2h_ms += ms;
+        }
+        float ms = 0;
+        for (int64_t t0 = 0; t0 < std::min<int64_t>(kRunStreams, n_tiles); ++t0)
+            for (int64_t t = 0; t < n_tiles; ++t)
+                if (cudaEventElapsedTime(&ms, ev[(size_t)t0].kb0, ev[(size_t)t].kb1) == cudaSuccess)
+                    st.bulk_span_ms = std::max(st.bulk_span_ms, (double)ms);
+        if (cudaEventElapsedTime(&ms, ev_begin, ev_end) == cudaSuccess) st.gpu_ms = ms;
+        st.pool_wait_ms = pool_wait_ms;
+        st.main_cell_days = nc * nd;
+        st.kernel_launches = launches;
+        st.n_tiles = n_tiles;
+        st.tile_cells = tile;
+        return SPLASH_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
 
 int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts* opts_in, splash_grid_out* out) {
     if (!ctx) return SPLASH_ERR_BAD_ARG;
@@ -974,8 +1633,6 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
     if (out->n_out != n_out)
         return fail(ctx, SPLASH_ERR_BAD_ARG, "out->n_out is %lld, expected %lld", (long long)out->n_out, (long long)n_out);
     if (opts.skip_spinup && !opts.state_init) return fail(ctx, SPLASH_ERR_BAD_ARG, "skip_spinup needs state_init");
-    const int max_spin = opts.max_spin > 0 ? opts.max_spin : 1000;
-    const double spin_tol = opts.spin_tol_mm > 0 ? opts.spin_tol_mm : 1.0;
     if (nc == 0) return SPLASH_OK;
 
     CU(cudaSetDevice(ctx->device));
@@ -1013,282 +1670,47 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
     }
     if (int rc = ensure(ctx, ctx->dtab, sizeof(DayTab) * h_tab.size())) return rc;
     if (int rc = ensure(ctx, ctx->dtab_spin, sizeof(DayTab) * kSpinYear)) return rc;
-    CU(cudaMemcpyAsync(ctx->dtab.p, h_tab.data(), sizeof(DayTab) * h_tab.size(), cudaMemcpyHostToDevice, ctx->s_run));
-    CU(cudaMemcpyAsync(ctx->dtab_spin.p, h_spin.data(), sizeof(DayTab) * kSpinYear, cudaMemcpyHostToDevice, ctx->s_run));
-    CU(cudaStreamSynchronize(ctx->s_run));
+    CU(cudaMemcpyAsync(ctx->dtab.p, h_tab.data(), sizeof(DayTab) * h_tab.size(), cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaMemcpyAsync(ctx->dtab_spin.p, h_spin.data(), sizeof(DayTab) * kSpinYear, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_h2d));
 
-    const bool in_dev = (in->mem_kind == SPLASH_MEM_DEVICE);
-    const bool out_dev = (out->mem_kind == SPLASH_MEM_DEVICE);
-    const size_t fsz = in->forcing_dtype == SPLASH_F32 ? 4 : 8;
-    double* const out_ptr[9] = {out->wn, out->ro, out->pet, out->aet, out->snow, out->cond, out->bflow, out->netr, out->sm_lim};
-    int n_out_layers = 0;
-    for (int k = 0; k < 9; ++k) n_out_layers += out_ptr[k] ? 1 : 0;
-
-    // ---- tile size ------------------------------------------------------------------------------------
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    size_t held = 0;  // bytes already held by this context's grow-only buffers count as available
-    for (int i = 0; i < kSlots; ++i) {
-        for (int k = 0; k < 3; ++k) held += ctx->forcing[i][k].cap;
-        held += ctx->cellin[i].cap + ctx->cc[i].cap + ctx->outs[i].cap + ctx->work_d[i].cap + ctx->work_i[i].cap + ctx->diag[i].cap;
-    }
-    const double budget = 0.80 * (double)(free_b + held);
-    double per_cell = (double)(NCC + 11 + SPLASH_NDIAG + 14) * 8.0 + 6 * 4.0;
-    if (!in_dev) per_cell += 3.0 * (double)nd * (double)fsz;
-    if (!out_dev) per_cell += (double)n_out_layers * (double)n_out * 8.0;
-    int64_t tile = opts.tile_cells > 0 ? opts.tile_cells : (int64_t)(budget / ((double)kSlots * per_cell));
-    tile = std::min<int64_t>(tile, nc);
-    if (tile < nc) {
-        int64_t t2 = tile / 1024 * 1024;
-        if (t2 == 0) t2 = tile / kThreads * kThreads;
-        tile = std::max<int64_t>(kThreads, t2);
-    }
-    if (tile <= 0) return fail(ctx, SPLASH_ERR_NOMEM, "not enough device memory for one tile");
-    if (tile > (int64_t)INT32_MAX / 2) tile = (int64_t)INT32_MAX / 2 / 1024 * 1024;
-    const int64_t n_tiles = (nc + tile - 1) / tile;
-    const int64_t pitch = round_up(tile, 32);
-
-    // ---- per-tile timing events and final counters ----------------------------------------------------------
-    struct TileEv {
-        cudaEvent_t c0, c1;          // h2d stream: begin / end of the tile's uploads
-        cudaEvent_t k0, k1, k2, kb, k3;  // run stream: begin, setup done, bulk launch, bulk done, all kernels done
-        cudaEvent_t o0, o1;          // d2h stream: begin / end of the tile's downloads
-    };
-    std::vector<TileEv> tev((size_t)n_tiles);
-    for (auto& t : tev) {
-        cudaEvent_t* evs[9] = {&t.c0, &t.c1, &t.k0, &t.k1, &t.k2, &t.kb, &t.k3, &t.o0, &t.o1};
-        for (auto* e : evs) CU(cudaEventCreate(e));
-    }
-    unsigned long long* h_final = nullptr;
-    CU(cudaMallocHost(&h_final, sizeof(unsigned long long) * NCOUNTERS * (size_t)n_tiles));
-    memset(h_final, 0, sizeof(unsigned long long) * NCOUNTERS * (size_t)n_tiles);
-    int64_t launches = 0;
-    bool slot_used[kSlots] = {false, false};
-
-    struct TileDev {
-        const void* d_force[3];
-        int64_t fpitch;
-        SetupParams sp;
-    };
-    std::vector<TileDev> tdev((size_t)n_tiles);
-
-    // uploads of tile t (enqueued one tile ahead of its kernels)
-    auto enqueue_h2d = [&](int64_t t) -> int {
-        const int s = (int)(t % kSlots);
-        const int64_t c0 = t * tile;
-        const int64_t nct = std::min<int64_t>(tile, nc - c0);
-        TileDev& td = tdev[(size_t)t];
-        SetupParams& sp = td.sp;
-        sp = SetupParams{};
-        if (in_dev) {
-            const char* base[3] = {(const char*)in->sw_in, (const char*)in->tc, (const char*)in->pn};
-            for (int k = 0; k < 3; ++k) td.d_force[k] = base[k] + (size_t)c0 * fsz;
-            td.fpitch = istride;
-            sp.lat = in->lat + c0;
-            sp.elev = in->elev + c0;
-            sp.slop = in->slop + c0;
-            sp.asp = in->asp + c0;
-            sp.resolution = in->resolution + c0;
-            sp.soil = in->soil + c0;
-            sp.soil_pitch = nc;
-            sp.au = in->au + c0;
-            sp.au_pitch = nc;
-            CU(cudaEventRecord(tev[(size_t)t].c0, ctx->s_h2d));
-            CU(cudaEventRecord(tev[(size_t)t].c1, ctx->s_h2d));
-        } else {
-            for (int k = 0; k < 3; ++k)
-                if (int rc = ensure(ctx, ctx->forcing[s][k], (size_t)std::max<int64_t>(nd, 1) * pitch * fsz)) return rc;
-            if (int rc = ensure(ctx, ctx->cellin[s], (size_t)(5 + 6 + 3) * pitch * 8)) return rc;
-            if (slot_used[s]) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_run[s], 0));  // slot's previous kernels done
-            CU(cudaEventRecord(tev[(size_t)t].c0, ctx->s_h2d));
-            const char* src[3] = {(const char*)in->sw_in, (const char*)in->tc, (const char*)in->pn};
-            for (int k = 0; k < 3; ++k) {
-                if (nd > 0)
-                    CU(cudaMemcpy2DAsync(ctx->forcing[s][k].p, (size_t)pitch * fsz, src[k] + (size_t)c0 * fsz,
-                                         (size_t)istride * fsz, (size_t)nct * fsz, (size_t)nd, cudaMemcpyHostToDevice,
-                                         ctx->s_h2d));
-                td.d_force[k] = ctx->forcing[s][k].p;
-                ctx->stats.h2d_bytes += (int64_t)nct * nd * (int64_t)fsz;
-            }
-            td.fpitch = pitch;
-            double* ci = (double*)ctx->cellin[s].p;
-            const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
-            for (int k = 0; k < 5; ++k)
-                CU(cudaMemcpyAsync(ci + (size_t)k * pitch, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
-            CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6,
-                                 cudaMemcpyHostToDevice, ctx->s_h2d));
-            CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8,
-                                 (size_t)in->au_layers, cudaMemcpyHostToDevice, ctx->s_h2d));
-            ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
-            sp.lat = ci;
-            sp.elev = ci + pitch;
-            sp.slop = ci + 2 * pitch;
-            sp.asp = ci + 3 * pitch;
-            sp.resolution = ci + 4 * pitch;
-            sp.soil = ci + 5 * pitch;
-            sp.soil_pitch = pitch;
-            sp.au = ci + 11 * pitch;
-            sp.au_pitch = pitch;
-            CU(cudaEventRecord(tev[(size_t)t].c1, ctx->s_h2d));
+    auto fill = [&](auto& job) {
+        job.ctx = ctx;
+        job.in = in;
+        job.out = out;
+        job.opts = opts;
+        job.nc = nc;
+        job.nd = nd;
+        job.n_out = n_out;
+        job.istride = istride;
+        job.ostride = ostride;
+        job.in_dev = (in->mem_kind == SPLASH_MEM_DEVICE);
+        job.out_dev = (out->mem_kind == SPLASH_MEM_DEVICE);
+        job.monthly = opts.monthly_out != 0;
+        job.max_spin = opts.max_spin > 0 ? opts.max_spin : 1000;
+        job.spin_tol = opts.spin_tol_mm > 0 ? opts.spin_tol_mm : 1.0;
+        double* const op[9] = {out->wn, out->ro, out->pet, out->aet, out->snow, out->cond, out->bflow, out->netr, out->sm_lim};
+        for (int k = 0; k < 9; ++k) {
+            job.out_ptr[k] = op[k];
+            job.n_out_layers += op[k] ? 1 : 0;
         }
-        CU(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
-        return SPLASH_OK;
     };
-
-    auto run_tiles = [&]() -> int {
-        if (int rc = enqueue_h2d(0)) return rc;
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            const int s = (int)(t % kSlots);
-            const int64_t c0 = t * tile;
-            const int64_t nct = std::min<int64_t>(tile, nc - c0);
-            TileEv& ev = tev[(size_t)t];
-            TileDev& td = tdev[(size_t)t];
-            // ---- device buffers of this slot ---------------------------------------------------------------
-            if (int rc = ensure(ctx, ctx->cc[s], (size_t)NCC * pitch * 8)) return rc;
-            if (!out_dev && n_out_layers)
-                if (int rc = ensure(ctx, ctx->outs[s], (size_t)n_out_layers * std::max<int64_t>(n_out, 1) * pitch * 8)) return rc;
-            if (int rc = ensure(ctx, ctx->work_d[s], (size_t)11 * pitch * 8)) return rc;
-            if (int rc = ensure(ctx, ctx->work_i[s], (size_t)6 * pitch * 4)) return rc;
-            if (int rc = ensure(ctx, ctx->diag[s], (size_t)SPLASH_NDIAG * pitch * 8)) return rc;
-            if (int rc = ensure(ctx, ctx->counters[s], sizeof(unsigned long long) * NCOUNTERS)) return rc;
-
-            // ---- kernels -----------------------------------------------------------------------------------
-            CU(cudaStreamWaitEvent(ctx->s_run, ctx->ev_h2d[s], 0));
-            if (slot_used[s]) CU(cudaStreamWaitEvent(ctx->s_run, ctx->ev_d2h[s], 0));  // slot's previous outputs copied out
-            CU(cudaEventRecord(ev.k0, ctx->s_run));
-            double* d_diag = (double*)ctx->diag[s].p;
-            SetupParams sp = td.sp;
-            sp.au_layers = in->au_layers;
-            sp.n_cells = (int)nct;
-            sp.cc = (double*)ctx->cc[s].p;
-            sp.cpitch = pitch;
-            sp.diag = d_diag;
-            sp.dpitch = pitch;
-
-            RunParams rp{};
-            rp.sw = td.d_force[0];
-            rp.tc = td.d_force[1];
-            rp.pn = td.d_force[2];
-            rp.fpitch = td.fpitch;
-            rp.cc = sp.cc;
-            rp.cpitch = pitch;
-            rp.dtab = (const DayTab*)ctx->dtab.p;
-            rp.dtab_spin = (const DayTab*)ctx->dtab_spin.p;
-            rp.n_days = (int)nd;
-            rp.n_cells = (int)nct;
-            double* wd = (double*)ctx->work_d[s].p;
-            int* wi = (int*)ctx->work_i[s].p;
-            rp.w.st = wd;
-            rp.w.w1 = wd + 5 * pitch;
-            rp.w.snap = wd + 6 * pitch;
-            rp.w.passes = wi;
-            rp.w.snap_pass = wi + pitch;
-            rp.w.status = wi + 2 * pitch;
-            rp.w.pitch = pitch;
-            int li = 0;
-            for (int k = 0; k < 9; ++k) {
-                if (!out_ptr[k]) {
-                    rp.out[k] = nullptr;
-                } else if (out_dev) {
-                    rp.out[k] = out_ptr[k] + c0;
-                } else {
-                    rp.out[k] = (double*)ctx->outs[s].p + (size_t)li * std::max<int64_t>(n_out, 1) * pitch;
-                    ++li;
-                }
-            }
-            rp.opitch = out_dev ? ostride : pitch;
-            rp.diag = d_diag;
-            rp.dpitch = pitch;
-            rp.max_spin = max_spin;
-            rp.spin_tol = spin_tol;
-            rp.counters = (unsigned long long*)ctx->counters[s].p;
-
-            // the next tile's uploads go out before this tile's kernel sequence blocks the host
-            if (t + 1 < n_tiles) {
-                slot_used[s] = true;  // (slot of tile t is in use from here on)
-                if (int rc = enqueue_h2d(t + 1)) return rc;
-            }
-            int rc;
-            if (in->forcing_dtype == SPLASH_F32)
-                rc = run_tile_kernels<float>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2, ev.kb);
-            else
-                rc = run_tile_kernels<double>(ctx, s, rp, sp, opts, opts.state_init, c0, nc, pitch, &launches, ev.k1, ev.k2, ev.kb);
-            if (rc) return rc;
-            CU(cudaEventRecord(ev.k3, ctx->s_run));
-            CU(cudaMemcpyAsync(h_final + (size_t)t * NCOUNTERS, ctx->counters[s].p, sizeof(unsigned long long) * NCOUNTERS,
-                               cudaMemcpyDeviceToHost, ctx->s_run));
-            CU(cudaEventRecord(ctx->ev_run[s], ctx->s_run));
-
-            // ---- D2H -----------------------------------------------------------------------------------
-            CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_run[s], 0));
-            CU(cudaEventRecord(ev.o0, ctx->s_d2h));
-            const cudaMemcpyKind okind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-            if (!out_dev) {
-                for (int k = 0; k < 9; ++k) {
-                    if (!out_ptr[k] || n_out == 0) continue;
-                    CU(cudaMemcpy2DAsync(out_ptr[k] + c0, (size_t)ostride * 8, rp.out[k], (size_t)pitch * 8, (size_t)nct * 8,
-                                         (size_t)n_out, cudaMemcpyDeviceToHost, ctx->s_d2h));
-                    ctx->stats.d2h_bytes += (int64_t)nct * n_out * 8;
-                }
-            }
-            if (out->state_final) {
-                CU(cudaMemcpy2DAsync(out->state_final + c0, (size_t)nc * 8, rp.w.st, (size_t)pitch * 8, (size_t)nct * 8, 5, okind,
-                                     ctx->s_d2h));
-                if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * 5 * 8;
-            }
-            if (out->cell_diag) {
-                CU(cudaMemcpy2DAsync(out->cell_diag + c0, (size_t)nc * 8, d_diag, (size_t)pitch * 8, (size_t)nct * 8, SPLASH_NDIAG,
-                                     okind, ctx->s_d2h));
-                if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * SPLASH_NDIAG * 8;
-            }
-            CU(cudaEventRecord(ev.o1, ctx->s_d2h));
-            CU(cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h));
-            slot_used[s] = true;
-        }
-        CU(cudaStreamSynchronize(ctx->s_h2d));
-        CU(cudaStreamSynchronize(ctx->s_run));
-        CU(cudaStreamSynchronize(ctx->s_aux));
-        CU(cudaStreamSynchronize(ctx->s_d2h));
-        return SPLASH_OK;
-    };
-    const int rc_all = run_tiles();
-    double t_h2d = 0, t_setup = 0, t_spin = 0, t_main = 0, t_bulk = 0, t_d2h = 0;
-    if (rc_all == SPLASH_OK) {
-        for (auto& t : tev) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, t.c0, t.c1) == cudaSuccess) t_h2d += ms;
-            if (cudaEventElapsedTime(&ms, t.k0, t.k1) == cudaSuccess) t_setup += ms;
-            if (cudaEventElapsedTime(&ms, t.k1, t.k2) == cudaSuccess) t_spin += ms;
-            if (cudaEventElapsedTime(&ms, t.k2, t.k3) == cudaSuccess) t_main += ms;
-            if (cudaEventElapsedTime(&ms, t.k2, t.kb) == cudaSuccess) t_bulk += ms;
-            if (cudaEventElapsedTime(&ms, t.o0, t.o1) == cudaSuccess) t_d2h += ms;
-        }
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            ctx->stats.spin_cell_days += (int64_t)h_final[(size_t)t * NCOUNTERS + CNT_SPIN_DAYS];
-            ctx->stats.unconverged_cells += (int64_t)h_final[(size_t)t * NCOUNTERS + CNT_UNCONVERGED];
-            ctx->stats.cycle_cells += (int64_t)h_final[(size_t)t * NCOUNTERS + CNT_CYCLES];
-        }
+    int rc;
+    if (in->forcing_dtype == SPLASH_F32) {
+        GridJob<float> job{};
+        fill(job);
+        rc = job.run();
+        if (rc != SPLASH_OK) cudaDeviceSynchronize();
+        job.release();
     } else {
-        cudaDeviceSynchronize();
+        GridJob<double> job{};
+        fill(job);
+        rc = job.run();
+        if (rc != SPLASH_OK) cudaDeviceSynchronize();
+        job.release();
     }
-    for (auto& t : tev) {
-        cudaEvent_t evs[9] = {t.c0, t.c1, t.k0, t.k1, t.k2, t.kb, t.k3, t.o0, t.o1};
-        for (auto e : evs) cudaEventDestroy(e);
-    }
-    cudaFreeHost(h_final);
-    if (rc_all != SPLASH_OK) return rc_all;
-
-    ctx->stats.h2d_ms = t_h2d;
-    ctx->stats.setup_ms = t_setup;
-    ctx->stats.spinup_ms = t_spin;  // up to the launch of the bulk daily kernel
-    ctx->stats.main_ms = t_main;    // bulk daily kernel with the straggler tail running beside it
-    ctx->stats.bulk_ms = t_bulk;
-    ctx->stats.d2h_ms = t_d2h;
-    ctx->stats.main_cell_days = nc * nd;
-    ctx->stats.kernel_launches = launches;
-    ctx->stats.n_tiles = n_tiles;
-    ctx->stats.total_ms =
-        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (rc != SPLASH_OK) return rc;
+    ctx->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return SPLASH_OK;
 }
 

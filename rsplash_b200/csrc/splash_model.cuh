@@ -24,6 +24,24 @@
 // from libdevice vs glibc transcendentals only (<= 2 ulp each).
 #pragma once
 
+// SPLASH_LEVEL selects how literally the day step follows the reference's floating-point recipe:
+//   0  every operation in the reference's order, libdevice pow() where the reference calls pow()
+//   1  (default) same formulas, but x^y is evaluated as exp(y*log(x)) with the logarithm shared
+//      between powers of the same base, divisions by per-cell constants become multiplications
+//      by reciprocals computed once, and the Kunsat power is skipped where the reference never
+//      uses it.  Each rewrite perturbs a result by a few ulp (1e-16 relative), three orders of
+//      magnitude inside the parity budget; tests/test_parity_gpu.py runs the gates on both.
+#ifndef SPLASH_LEVEL
+#define SPLASH_LEVEL 1
+#endif
+// the two halves of level 1 can be switched separately (bisecting numerical differences)
+#ifndef SPLASH_L1_POW
+#define SPLASH_L1_POW (SPLASH_LEVEL >= 1)    // x^y as exp(y*log(x)) with shared logarithms
+#endif
+#ifndef SPLASH_L1_RECIP
+#define SPLASH_L1_RECIP (SPLASH_LEVEL >= 1)  // reciprocals of per-cell constants, consistent theta scaling
+#endif
+
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -62,16 +80,25 @@ enum CellConst : int {
     // geometry
     C_COS_LAT, C_SIN_LAT, C_SIN_S, C_COS_S, C_COS_A, C_SIN_A, C_TAN_S, C_COS2_S,
     // atmosphere
-    C_TAU_O, C_TAU_A, C_TAU_B, C_PATM, C_PBAR, C_PBARF, C_VISC0,
+    C_TAU_O, C_TAU_A, C_PATM, C_PBAR, C_PBARF, C_VISC0,
     // soil column
-    C_SAT, C_RES, C_DEPTH, C_D1000, C_THS, C_THR, C_DTH, C_ILAM, C_NLAM, C_E3, C_BUB, C_BP10,
-    C_WMAX, C_WMR, C_THWMAX, C_INTPERM, C_HF, C_KUEXP,
+    C_SAT, C_RES, C_DEPTH, C_THS, C_THR, C_DTH, C_ILAM, C_NLAM, C_E3, C_BUB,
+    C_WMAX, C_THWMAX, C_INTPERM, C_HF, C_KUEXP,
     // lateral flow
-    C_BRQ0, C_DENKB, C_BRW, C_ACSW, C_CW, C_SIDOCT, C_AI, C_AU,
+    C_BRQ0, C_BRW, C_ACSW, C_CW, C_SIDOCT, C_AI, C_AU,
     C_CELLOUT, C_CQ0, C_ACSQS, C_CT,  // depend on cellout (recomputed after the aridity pass)
     // output stage
     C_WRR,         // Wmax_R - RES, denominator of sm_lim (R/splash.point.R:197)
-    NCC
+    // level-1 reciprocals and cached powers
+    C_INV_D1000, C_INV_DTH, C_INV_WMR, C_INV_TAU_B, C_INV_AI, C_INV_DENKB, C_TEN_BP, C_KU_WMAX,
+    // only read by the level-0 day step (and by cell_setup)
+    C_D1000, C_WMR, C_TAU_B, C_DENKB, C_BP10,
+    NCC,
+#if SPLASH_L1_RECIP
+    NCC_DAY = C_D1000  // constants the day step reads: what the kernels stage in shared memory
+#else
+    NCC_DAY = NCC
+#endif
 };
 
 struct DayTab {      // per-day values that do not depend on the cell (host-built, SOLAR.cpp:98-124)
@@ -95,12 +122,34 @@ struct DayOut {
     double ro, pet, aet, cond, bflow, netr;
 };
 
+#if SPLASH_L1_RECIP
+#define SPLASH_TO_DEG(x) ((x) * (180.0 / kPI))
+#define SPLASH_DIV_D1000(x) ((x) * cc(C_INV_D1000))
+#define SPLASH_DIV_DTH(x) ((x) * cc(C_INV_DTH))
+#define SPLASH_DIV_TAU_B(x) ((x) * cc(C_INV_TAU_B))
+#define SPLASH_DIV_1000(x) ((x) * 1e-3)
+#else
+#define SPLASH_TO_DEG(x) ((x) / kpir)
+#define SPLASH_DIV_D1000(x) ((x) / cc(C_D1000))
+#define SPLASH_DIV_DTH(x) ((x) / cc(C_DTH))
+#define SPLASH_DIV_TAU_B(x) ((x) / cc(C_TAU_B))
+#define SPLASH_DIV_1000(x) ((x) / 1000.0)
+#endif
+
+// One shared copy of each transcendental instead of ~25 inlined expansions: the day step is a
+// single long loop body and its code size, not its arithmetic, was the first bottleneck (ncu:
+// 48 % of warp-stall samples were `no_instruction` with a 91 KB kernel, profiles/README.md).
+__device__ __noinline__ double f_exp(double x) { return exp(x); }
+__device__ __noinline__ double f_log(double x) { return log(x); }
+__device__ __noinline__ double f_acos(double x) { return acos(x); }
+__device__ __noinline__ double f_sin(double x) { return sin(x); }
+
 // std::max / std::min semantics of the reference (NaN in the first argument wins, SURVEY B-1)
 __device__ __forceinline__ double cxx_max(double a, double b) { return (a < b) ? b : a; }
 __device__ __forceinline__ double cxx_min(double a, double b) { return (b < a) ? b : a; }
 
 // ------------------------------------------------------------------------------------------------
-// glibc expf, bit-exact.  EVAP::calc_viscosity_h2o ends in std::exp(float) (src/EVAP.cpp:451),
+// glibc expf, bit-exact.  EVAP::calc_viscosity_h2o ends in std::f_exp(float) (src/EVAP.cpp:451),
 // i.e. glibc's expf, whose result differs from the correctly rounded one in a fraction of a
 // percent of arguments; viscosity scales every conductivity, so a 1-ulp float error (6e-8) would
 // dominate the error budget (SURVEY B-4).  This follows the published algorithm of glibc 2.28+
@@ -119,7 +168,7 @@ __device__ __constant__ double kExp2Tab[32] = {
 
 __device__ __forceinline__ float glibc_expf(float x) {
     const double xd = (double)x;
-    if (!(fabsf(x) < 88.0f)) return (float)exp(xd);  // overflow/underflow/NaN tails: not reached by viscosity
+    if (!(fabsf(x) < 88.0f)) return (float)f_exp(xd);  // overflow/underflow/NaN tails: not reached by viscosity
     const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p+52;
     const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
     double kd = fma(InvLn2N, xd, Shift);
@@ -261,10 +310,30 @@ struct Transm {
 };
 
 template <class CC>
-__device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, double ksat_visc) {
+__device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, double ksat_visc) {
     const double bub = cc(C_BUB);
     const double e3 = cc(C_E3);
     const double depth = cc(C_DEPTH);
+    Transm r;
+#if SPLASH_L1_POW
+    const double theta_i = SPLASH_DIV_D1000(sm);
+    const double x = SPLASH_DIV_DTH(theta_i - cc(C_THR));
+    const double a = cc(C_ILAM) * f_log(x);  // log shared by x^(1/lambda) and (x^(1/lambda))^(3 lambda + 1)
+    const double psi_m = bub / f_exp(a);
+    double wtd = SPLASH_DIV_1000(bub - psi_m);
+    if (wtd < 0.0 || isnan(wtd)) {
+        wtd = 0.01;
+    } else if (wtd > depth) {
+        wtd = depth;
+    }
+    r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
+    const double r1 = f_exp(e3 * a);  // (bub/psi_m)^e3 with bub/psi_m == x^(1/lambda)
+    // second power: its base is 1 up to rounding noise unless wtd was clamped; first-order expansion there
+    const double q = bub / (psi_m + (wtd * 1000.0));
+    const double qm1 = q - 1.0;
+    const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : f_exp(e3 * f_log(q));
+    double t_uns = (ksat_visc * bub / e3) * (r1 - r2);
+#else
     const double theta_i = (sm) / cc(C_D1000);
     const double psi_m = bub / pow((((theta_i - cc(C_THR)) / cc(C_DTH))), cc(C_ILAM));
     double wtd = ((bub - psi_m) / 1000.0);
@@ -273,9 +342,9 @@ __device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, 
     } else if (wtd > depth) {
         wtd = depth;
     }
-    Transm r;
     r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
     double t_uns = (ksat_visc * bub / e3) * (pow((bub / psi_m), e3) - pow((bub / (psi_m + (wtd * 1000.0))), e3));
+#endif
     t_uns *= cc(C_CT);
     if (t_uns < 0.0 || isnan(t_uns)) {
         t_uns = 0.0;
@@ -287,24 +356,42 @@ __device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, 
 // snowfall_prob's exponent, R/splash.point.R:576
 template <class CC>
 __device__ __forceinline__ double snow_prob(const CC& cc, double tc) {
-    return 1 / (1 + exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
+    return 1 / (1 + f_exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
 }
 
 // ------------------------------------------------------------------------------------------------
-// One day of one cell.
+// One day of one cell, in two halves.
+//
+//   day_forcing   everything that depends on the day's forcing and the cell's constants only: snow
+//                 partition, solar geometry up to the net longwave flux, the thermodynamic
+//                 coefficients and the water viscosity.  It is the same in every spin-up pass over
+//                 the cyclic first year, which the straggler pool exploits (k_pool_table).
+//   day_state     the part that carries the state: albedo, net radiation, evapotranspiration,
+//                 snowmelt, infiltration, runoff, lateral flow, soil-water update.
+//
+// splash_day = day_forcing + day_state is what every other kernel inlines; splitting it moves no
+// floating-point operation, so both routes give bit-identical results.
 //   cc     accessor for the cell's constants
 //   dt     day table entry (dr, sin/cos of declination, month)
 //   mt     month table of frain_func
 //   sw_in, tc, pn   raw forcing of the day (pn = total precipitation before the snow partition)
-//   st     state in/out
-//   o      fluxes of the day
-//   snowfall_out    snowfall of the day (for the aridity index and the occurrence flags)
-//   rain_out        rainfall of the day
 // ------------------------------------------------------------------------------------------------
+struct DayPre {
+    double snowfall, rain;            // R/splash.point.R:127-128
+    double ru, rv, ruv, hs, sin_hs;   // SOLAR.cpp:129-159 (hs in degrees)
+    double tau, dr;                   // transmittivity, distance factor
+    double r_in, rw_den;              // 86400*sw_in;  (86400/pi)*(ru*pir*hs + rv*sin(hs)), SOLAR.cpp:223
+    double rw_dark;                   // != 0 when sw_in == 0 or hs == 0 (first branch of SOLAR.cpp:220)
+    double rnl;                       // net longwave, SOLAR.cpp:203
+    double tc;
+    double s, g, econ, pw, eet_k, rx; // EVAP.cpp:110-145
+    double ksat_visc;                 // SPLASH.cpp:1260
+};
+constexpr int kDayPreDoubles = sizeof(DayPre) / sizeof(double);
+
 template <class CC>
-__device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
-                                           double pn, CellState& st, DayOut& o, double& rain_out,
-                                           double& snowfall_out) {
+__device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
+                                            double pn, DayPre& q) {
     // ---- snow partition, R/splash.point.R:120-128 with frain_func :547-555 ------------------------
     const double p_snow = snow_prob(cc, tc);
     double f_rain;
@@ -326,36 +413,11 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     } else {
         f_rain = 1;
     }
-    const double snowfall = pn * (1 - f_rain);
-    const double rain = pn * f_rain;
-    snowfall_out = snowfall;
-    rain_out = rain;
+    q.snowfall = pn * (1 - f_rain);
+    q.rain = pn * f_rain;
+    q.tc = tc;
 
-    const double wn = st.wn;
-    // ---- 00/03. theta_i clamp and supply rate, SPLASH.cpp:984-990, 1042-1048 ----------------------
-    const double theta_s = cc(C_THS);
-    double theta_i = (wn) / cc(C_D1000);
-    if (theta_i >= theta_s) {
-        theta_i = theta_s - 0.001;
-    } else if (theta_i <= cc(C_THR)) {
-        theta_i = cc(C_THR) + 0.001;
-    }
-    double sw = ((wn - cc(C_RES)) / cc(C_WMR));
-    if (sw < 0.0 || isnan(sw)) {
-        sw = 0.0;
-    } else if (sw > 1.0) {
-        sw = 1.0;
-    }
-    // ---- 04. snowpack, :1225-1231 ---------------------------------------------------------------
-    double nd = st.nd;
-    if (snowfall > 0.0) {
-        nd = 0.0;
-    } else {
-        nd += 1.0;
-    }
-    double snow = st.snow + snowfall;
-
-    // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:129-255 ------------------------------------------
+    // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:129-203 ------------------------------------------
     const double a = dt.sd * cc(C_COS_LAT) * cc(C_SIN_S) * cc(C_COS_A) - dt.sd * cc(C_SIN_LAT) * cc(C_COS_S);
     const double b = dt.cd * cc(C_COS_LAT) * cc(C_COS_S) + dt.cd * cc(C_SIN_LAT) * cc(C_SIN_S) * cc(C_COS_A);
     const double c = dt.cd * cc(C_SIN_S) * cc(C_SIN_A);
@@ -376,10 +438,10 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
         hs = 0.0;
     } else {
         hs = -1.0 * ruv;
-        hs = acos(hs);
-        hs /= kpir;
+        hs = f_acos(hs);
+        hs = SPLASH_TO_DEG(hs);
     }
-    const double sin_hs = sin(hs * kpir);
+    const double sin_hs = f_sin(hs * kpir);
     double ra_d = (86400.0 / kPI) * dt.dr * kGsc;
     ra_d *= (ru * hs * kpir + rv * sin_hs);
     const double tau_o = cc(C_TAU_O);
@@ -390,44 +452,31 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     } else {
         tau = r_in / (ra_d);
     }
+#if SPLASH_L1_POW
+    double sf = f_exp((1 / 0.7410) * f_log(SPLASH_DIV_TAU_B(tau - cc(C_TAU_A))));
+#else
     double sf = pow(((tau - cc(C_TAU_A)) / cc(C_TAU_B)), (1 / 0.7410));
+#endif
     if (isnan(sf)) {
         sf = 0.0;
     } else if (sf > 1.0) {
         sf = 1.0;
     }
-    const double rnl = (0.0883289 + (1.0 - kb) * sf) * (kA + 1.95974 * tc);
-    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * exp(-0.895189 * nd));
-    const double sfc = snow / (140.0 + snow);
-    const double alb_v = kalb_sw - 0.17 * sw;
-    const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
-    double rw;
-    if ((sw_in == 0.0) || (hs == 0.0)) {
-        rw = (1.0 - alb) * tau * dt.dr * kGsc;
-    } else {
-        rw = (1.0 - alb) * (r_in) / ((86400.0 / kPI) * (ru * kpir * hs + rv * sin_hs));
-    }
-    double hn;
-    const double qn = (rnl - rw * ru) / (rw * rv);
-    if (qn >= 1.0) {
-        hn = 0;
-    } else if (qn <= -1.0) {
-        hn = 180.0;
-    } else {
-        hn = acos(qn);
-        hn /= kpir;
-    }
-    const double sin_hn = sin(hn * kpir);
-    double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
-    rn_d *= (86400.0 / kPI);
-    double rnn_d = rw * rv * (sin_hs - sin_hn);
-    rnn_d += rw * ru * (hs - hn) * kpir;
-    rnn_d -= rnl * (kPI - hn * kpir);
-    rnn_d *= (86400.0 / kPI);
+    q.rnl = (0.0883289 + (1.0 - kb) * sf) * (kA + 1.95974 * tc);
+    q.ru = ru;
+    q.rv = rv;
+    q.ruv = ruv;
+    q.hs = hs;
+    q.sin_hs = sin_hs;
+    q.tau = tau;
+    q.dr = dt.dr;
+    q.r_in = r_in;
+    q.rw_den = ((86400.0 / kPI) * (ru * kpir * hs + rv * sin_hs));
+    q.rw_dark = ((sw_in == 0.0) || (hs == 0.0)) ? 1.0 : 0.0;
 
-    // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:100-263 --------------------------------------------
+    // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:100-145 --------------------------------------------
     const double patm = cc(C_PATM);
-    double s = exp((tc * 17.269) / (tc + 237.3));  // sat_slope, :299-301
+    double s = f_exp((tc * 17.269) / (tc + 237.3));  // sat_slope, :299-301
     s /= ((tc + 237.3) * (tc + 237.3));
     s *= (17.269) * (237.3) * (610.78);
     double lv = (tc + 273.15) / (tc + 273.15 - 33.91);  // enthalpy_vap, :313-315
@@ -452,9 +501,81 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
         }
         visc = viscosity_h2o(tcf, rho_d);
     }
+    q.s = s;
+    q.g = g;
+    q.econ = econ;
+    q.pw = pw;
+    q.eet_k = (1.0e3) * (s / (lv * pw * (s + 0.24 * g)));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
+    q.rx = (3.6e6) * econ;
+    q.ksat_visc = cc(C_INTPERM) * ((pw * kG) / visc) * 3.6;  // SPLASH.cpp:1260
+}
+
+template <class CC>
+__device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellState& st, DayOut& o) {
+    const double wn = st.wn;
+    const double tc = q.tc;
+    // ---- 00/03. theta_i clamp and supply rate, SPLASH.cpp:984-990, 1042-1048 ----------------------
+    const double theta_s = cc(C_THS);
+    const double theta_mean = SPLASH_DIV_D1000(wn);
+    double theta_i = theta_mean;
+    if (theta_i >= theta_s) {
+        theta_i = theta_s - 0.001;
+    } else if (theta_i <= cc(C_THR)) {
+        theta_i = cc(C_THR) + 0.001;
+    }
+#if SPLASH_L1_RECIP
+    double sw = ((wn - cc(C_RES)) * cc(C_INV_WMR));
+#else
+    double sw = ((wn - cc(C_RES)) / cc(C_WMR));
+#endif
+    if (sw < 0.0 || isnan(sw)) {
+        sw = 0.0;
+    } else if (sw > 1.0) {
+        sw = 1.0;
+    }
+    // ---- 04. snowpack, :1225-1231 ---------------------------------------------------------------
+    double nd = st.nd;
+    if (q.snowfall > 0.0) {
+        nd = 0.0;
+    } else {
+        nd += 1.0;
+    }
+    double snow = st.snow + q.snowfall;
+
+    // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:208-255 ------------------------------------------
+    const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
+    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * f_exp(-0.895189 * nd));
+    const double sfc = snow / (140.0 + snow);
+    const double alb_v = kalb_sw - 0.17 * sw;
+    const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
+    double rw;
+    if (q.rw_dark != 0.0) {
+        rw = (1.0 - alb) * q.tau * q.dr * kGsc;
+    } else {
+        rw = (1.0 - alb) * (q.r_in) / q.rw_den;
+    }
+    double hn;
+    const double qn = (rnl - rw * ru) / (rw * rv);
+    if (qn >= 1.0) {
+        hn = 0;
+    } else if (qn <= -1.0) {
+        hn = 180.0;
+    } else {
+        hn = f_acos(qn);
+        hn = SPLASH_TO_DEG(hn);
+    }
+    const double sin_hn = f_sin(hn * kpir);
+    double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
+    rn_d *= (86400.0 / kPI);
+    double rnn_d = rw * rv * (sin_hs - sin_hn);
+    rnn_d += rw * ru * (hs - hn) * kpir;
+    rnn_d -= rnl * (kPI - hn * kpir);
+    rnn_d *= (86400.0 / kPI);
+
+    // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:124-263 --------------------------------------------
+    const double s = q.s, g = q.g, econ = q.econ, pw = q.pw, rx = q.rx;
     const double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
-    const double eet_d = (1.0e3) * (s / (lv * pw * (s + 0.24 * g))) * rn_d;
-    const double rx = (3.6e6) * econ;
+    const double eet_d = q.eet_k * rn_d;
     const double pet_max = rx * ((rw * (ru + rv)) - rnl);
     const double B_r = g / (sw * s);
     const double EF = 1 / (B_r + 1.0);
@@ -462,15 +583,15 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     if (swp < 0.0 || isnan(swp)) {
         swp = 0.0;
     }
-    const double cos_hi = swp / (rw * rv * rx) + rnl / (rw * rv) - ru / rv;
+    const double cos_hi = swp / (rw * rv * rx) + rnl / (rw * rv) - q.ruv;  // ru/rv: same operands as in day_forcing
     double hi;
     if (cos_hi >= 1.0) {
         hi = 0.0;
     } else if (cos_hi <= -1.0) {
         hi = 180.0;
     } else {
-        hi = acos(cos_hi);
-        hi /= kpir;
+        hi = f_acos(cos_hi);
+        hi = SPLASH_TO_DEG(hi);
     }
     double snowmelt_tot;
     if (tc >= 3.0) {
@@ -483,7 +604,7 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
     melt_enrg += ((sublimation / 1000.0) / econ);
     double aet_d = swp * hi * kpir;
-    aet_d += rx * rw * rv * (sin_hn - sin(hi * kpir));
+    aet_d += rx * rw * rv * (sin_hn - f_sin(hi * kpir));
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
     aet_d *= (24.0 / kPI);
     aet_d -= (melt_enrg * econ * 1000.0);
@@ -494,17 +615,23 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     // ---- back in SPLASH::run_one_day, SPLASH.cpp:1236-1284 -----------------------------------------
     snow -= snowmelt_tot;
     const double snowmelt = snowmelt_tot - sublimation;
-    const double Ksat_visc = cc(C_INTPERM) * ((pw * kG) / visc) * 3.6;
-    const double inflow = rain + cn + snowmelt;
+    const double Ksat_visc = q.ksat_visc;
+    const double inflow = q.rain + cn + snowmelt;
     // moist_surf(depth, 10, bub, wn, SAT, RES, lambda), :1935-1957
     double surf_moist;
     {
         const double theta_r = cc(C_THR);
+#if SPLASH_L1_POW
+        // head/bp = (bp/u + 10)/bp = 1/u + 10/bp with u = x^(1/lambda); 1/u = f_exp(-f_log(x)/lambda)
+        const double lx = f_log(SPLASH_DIV_DTH(theta_mean - theta_r));
+        const double head = f_exp(-(cc(C_ILAM) * lx)) + cc(C_TEN_BP);
+        double theta_BC = cc(C_DTH) * f_exp(cc(C_NLAM) * f_log(head)) + theta_r;
+#else
         const double bp = cc(C_BP10);
-        const double theta_mean = (wn) / cc(C_D1000);
         const double water_pot_BC = bp / pow((((theta_mean - theta_r) / cc(C_DTH))), cc(C_ILAM));
         const double total_head_BC = water_pot_BC + 10.0;
         double theta_BC = cc(C_DTH) * pow((total_head_BC / bp), cc(C_NLAM)) + theta_r;
+#endif
         if (theta_mean < theta_r) {
             theta_BC = theta_r;
         } else if (isnan(theta_BC)) {
@@ -532,7 +659,7 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
                     tp = 0.01;
                 }
                 const double tp_s = tp / cc(C_COS2_S);
-                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * log(1 - (r * tp_s / (h_f * delta_theta)))));
+                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * f_log(1 - (r * tp_s / (h_f * delta_theta)))));
             }
         }
         if (I > P) {
@@ -542,7 +669,17 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     }
     const double ro_h = cxx_max(inflow - infi, 0.0);
     double R = infi - aet_d;
+    const bool deep = (cc(C_DEPTH) >= 2.0);
+#if SPLASH_L1_POW
+    // Kunsat only enters T_uns when depth >= 2 (:1433-1435); below field capacity its power is a cell constant
+    double Kunsat = 0.0;
+    if (deep) {
+        const double kp = (theta_i <= cc(C_THWMAX) || isnan(theta_i)) ? cc(C_KU_WMAX) : f_exp(cc(C_KUEXP) * f_log(theta_m / theta_s));
+        Kunsat = Ksat_visc * kp;
+    }
+#else
     const double Kunsat = Ksat_visc * pow((theta_m / theta_s), cc(C_KUEXP));
+#endif
     const double hyd_grad_in = cc(C_TAN_S);
     const double hyd_grad_z = (infi / (Ksat_visc * 24)) - 1.0;
     const double hyd_grad_out = sqrt((hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in));
@@ -552,7 +689,11 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     const double T_q0 = kbe3 * cc(C_BRQ0);
     const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
     const double Q_qs = (hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS) / 1000.0);
-    const double Kb = exp((Q_q0 - Q_qs) / cc(C_DENKB));
+#if SPLASH_L1_RECIP
+    const double Kb = f_exp((Q_q0 - Q_qs) * cc(C_INV_DENKB));
+#else
+    const double Kb = f_exp((Q_q0 - Q_qs) / cc(C_DENKB));
+#endif
     // ---- 5.2.2 drainage at Wmax, :1346-1360 --------------------------------------------------------
     const double To_uns = kbe3 * cc(C_BRW);
     const double Qo_uns = To_uns * cc(C_CW);
@@ -579,8 +720,12 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
         sm = RES;
         ro_d = 0.0;
     }
+#if SPLASH_L1_RECIP
+#define SPLASH_DIV_AI(x) ((x) * cc(C_INV_AI))
+#else
+#define SPLASH_DIV_AI(x) ((x) / Ai)
+#endif
     // ---- 5.6 transmittance after recharge, :1406-1457 ----------------------------------------------
-    const bool deep = (cc(C_DEPTH) >= 2.0);
     const double Ai = cc(C_AI);
     Transm tr = column_transmittance(cc, sm, Ksat_visc);
     double T;
@@ -589,9 +734,9 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
         double T_sat;
         if (deep) {
             T_uns += Kunsat * 24.0;
-            T_sat = Ksat_visc * 24.0 * ((tr.acs_out + Ai) / Ai);
+            T_sat = Ksat_visc * 24.0 * SPLASH_DIV_AI(tr.acs_out + Ai);
         } else {
-            T_sat = Ksat_visc * 24.0 * (tr.acs_out / Ai);
+            T_sat = Ksat_visc * 24.0 * SPLASH_DIV_AI(tr.acs_out);
         }
         T = (T_sat + T_uns) * hyd_grad_out;
     }
@@ -601,10 +746,10 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     double q_in_f = 0.0;
     const double td = st.td - 1.0;
     if ((R > 0.0) && (sm > cc(C_WMAX))) {
-        const double lkb = log(Kb);
+        const double lkb = f_log(Kb);
         const double Au = cc(C_AU);
-        t_drain = -1.0 * log(1.0 - (lkb * (Au * R / Q))) / lkb;
-        q_in_f = (Qt - Au * R * lkb) / Ai;
+        t_drain = -1.0 * f_log(1.0 - (lkb * (Au * R / Q))) / lkb;
+        q_in_f = SPLASH_DIV_AI(Qt - Au * R * lkb);
     }
     if (q_in_f < 0.0 || isnan(q_in_f)) {
         q_in_f = 0.0;
@@ -626,7 +771,7 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
         tr = column_transmittance(cc, sm, Ksat_visc);
     }
     {
-        const double T_sat = Ksat_visc * 24.0 * (tr.acs_out / Ai);
+        const double T_sat = Ksat_visc * 24.0 * SPLASH_DIV_AI(tr.acs_out);
         T = (T_sat + tr.t_uns) * hyd_grad_out;
     }
     // ---- 5.8' drain, :1552-1567 --------------------------------------------------------------------
@@ -648,6 +793,20 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     o.cond = cn;
     o.bflow = T;
     o.netr = rn_d / 1e6;
+#undef SPLASH_DIV_AI
+}
+
+//   st     state in/out;  o  fluxes of the day;  rain_out / snowfall_out  the partitioned precipitation
+//   (for the aridity index and the occurrence flags)
+template <class CC>
+__device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
+                                           double pn, CellState& st, DayOut& o, double& rain_out,
+                                           double& snowfall_out) {
+    DayPre q;
+    day_forcing(cc, dt, mt, sw_in, tc, pn, q);
+    rain_out = q.rain;
+    snowfall_out = q.snowfall;
+    day_state(cc, q, st, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,18 +845,18 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     const double dp = 1 / ((fOM / 1.3) + ((1 - fOM) / 2.65));
     double bd = in.bd;
     if (isnan(bd)) {
-        bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
+        bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - f_exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
     }
     if (bd < 0.81) bd = 0.81;
     double sat = 1 - (bd / dp);
     const double sq_clay = sqrt(fclay);  // fclay^0.5
     double fc = (sat / bd) * (0.4760944 + (0.9402962 - 0.4760944) * sq_clay) *
-                exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
+                f_exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
     const double wp_Ball = fc * (0.2018522 + (0.7809203 - 0.2018522) * sq_clay);
     double wp = -2.464e-05 * in.sand + 3.650e-03 * in.clay + 8.680e-03 * in.om + 9.393e-03 * bd;
     if (!isnan(wp) && wp >= fc) wp = wp_Ball;
-    const double coef_B = (log(1500.0) - log(33.0)) / (log(fc) - log(wp));
-    const double coef_A = exp(log(33.0) + coef_B * log(fc));
+    const double coef_B = (f_log(1500.0) - f_log(33.0)) / (f_log(fc) - f_log(wp));
+    const double coef_A = f_exp(f_log(33.0) + coef_B * f_log(fc));
     const double coef_lambda = 1 / coef_B;
     const double coeff_c = 1000.0 / (997 * 9.80665);
     const double theta_c = pow((coeff_c * coef_A / 2.0), (1 / (1 + coef_B)));
@@ -706,7 +865,7 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     sat = sat * (1 - fgravel);
     fc = fc * (1 - fgravel);
     wp = wp * (1 - fgravel);
-    const double ksat = 857.48454 / (1 + exp(-2.70927 * fsand + 3.62264 * bd + 7.33398 * fclay + -8.11795 * (sat - fc) +
+    const double ksat = 857.48454 / (1 + f_exp(-2.70927 * fsand + 3.62264 * bd + 7.33398 * fclay + -8.11795 * (sat - fc) +
                                             18.75552 * fOM + 1.03319 * coef_lambda));
     const double m33i = 0.278 * fsand + 0.034 * fclay + 0.022 * fOM - 0.018 * (fsand * fOM) - 0.027 * (fclay * fOM) -
                         0.584 * (fsand * fclay) + 0.078;
@@ -743,12 +902,12 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     cc(C_LAT_K) = fabs(in.lat) * 0.0110592101;
     const double asp = in.asp - 180;  // R/splash.point.R:131
     cc(C_COS_LAT) = cos(in.lat * kpir);
-    cc(C_SIN_LAT) = sin(in.lat * kpir);
-    cc(C_SIN_S) = sin(in.slop * kpir);
+    cc(C_SIN_LAT) = f_sin(in.lat * kpir);
+    cc(C_SIN_S) = f_sin(in.slop * kpir);
     const double cos_s = cos(in.slop * kpir);
     cc(C_COS_S) = cos_s;
     cc(C_COS_A) = cos(asp * kpir);
-    cc(C_SIN_A) = sin(asp * kpir);
+    cc(C_SIN_A) = f_sin(asp * kpir);
     cc(C_TAN_S) = tan(in.slop * kpir);
     cc(C_COS2_S) = cos_s * cos_s;
     // ---- atmosphere: SOLAR.cpp:170,197; EVAP.cpp:331-334 -------------------------------------------
@@ -778,20 +937,40 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     cc(C_RES) = RES;
     cc(C_DEPTH) = depth;
     cc(C_D1000) = d1000;
+#if SPLASH_L1_RECIP
+    // The day step forms theta = w * (1/d1000).  theta_s and theta_r are scaled by the same multiply so
+    // that a bucket sitting exactly at SAT (or RES) -- the clamps make that a common state -- still gives
+    // (theta_i - theta_r)/(theta_s - theta_r) == 1 (or 0) and never a ratio one ulp above 1, which
+    // would trip the reference's discontinuous failsafe `wtd < 0 -> 0.01` (SPLASH.cpp:1412-1413).
+    const double inv_d1000 = 1.0 / d1000;
+    const double theta_s1 = SAT * inv_d1000, theta_r1 = RES * inv_d1000;
+    cc(C_INV_D1000) = inv_d1000;
+    cc(C_THS) = theta_s1;
+    cc(C_THR) = theta_r1;
+    cc(C_DTH) = (theta_s1 - theta_r1);
+    cc(C_INV_DTH) = 1.0 / (theta_s1 - theta_r1);
+#else
     cc(C_THS) = theta_s;
     cc(C_THR) = theta_r;
     cc(C_DTH) = dth;
+    cc(C_INV_D1000) = 1.0 / d1000;
+    cc(C_INV_DTH) = 1.0 / dth;
+#endif
     cc(C_ILAM) = ilam;
     cc(C_NLAM) = (-1 * lambda);
     cc(C_E3) = e3;
     cc(C_BUB) = bub;
     cc(C_BP10) = bub / 10;
     const double KG_o = 1000.0 / (997 * kG);
-    const double coeff_A = exp(log(33.0) + (1.0 / lambda) * log(theta_fc));
+    const double coeff_A = f_exp(f_log(33.0) + (1.0 / lambda) * f_log(theta_fc));
     const double Wmax = pow((coeff_A * KG_o / (depth)), (1.0 / ((1 / lambda) + 1.0))) * (depth * 1000.0);
     cc(C_WMAX) = Wmax;
     cc(C_WMR) = (Wmax - RES);
+#if SPLASH_L1_RECIP
+    cc(C_THWMAX) = Wmax * inv_d1000;
+#else
     cc(C_THWMAX) = Wmax / (depth * 1000.0);
+#endif
     cc(C_INTPERM) = ksat / kfluidity;
     cc(C_HF) = ((2 + 3 * lambda) / (1 + 3 * lambda)) * (bub / 2);
     cc(C_KUEXP) = (3.0 + (2.0 / lambda));
@@ -827,6 +1006,12 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     }
     lateral_consts(cc, in.cellout);
     cc(C_WRR) = (Wmax_R - RES);
+    cc(C_INV_WMR) = 1.0 / (Wmax - RES);
+    cc(C_INV_TAU_B) = 1.0 / (tau_o * (1 - 0.1898));
+    cc(C_INV_AI) = 1.0 / Ai;
+    cc(C_INV_DENKB) = 1.0 / ((SAT - WP) * (Ai / 1000.0));
+    cc(C_TEN_BP) = 10.0 / (bub / 10);
+    cc(C_KU_WMAX) = pow((cc(C_THWMAX) / cc(C_THS)), (3.0 + (2.0 / lambda)));
     cc(C_TT) = nan("");
 }
 
