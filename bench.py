@@ -416,8 +416,11 @@ def main():
         hopts = _abi.SplashOpts()
         hopts.monthly_out = 1
 
+        block_stats = []
+
         def run_blocks(timed: bool):
             tot = 0.0
+            block_stats.clear()
             h2d = d2h = 0
             nl = 0
             for b in range(n_blocks):
@@ -447,6 +450,8 @@ def main():
                 h2d += s["h2d_bytes"]
                 d2h += s["d2h_bytes"]
                 nl += s["kernel_launches"]
+                block_stats.append({k: s[k] for k in ("total_ms", "gpu_ms", "h2d_ms", "d2h_ms", "pool_wait_ms", "scatter_ms", "first_ms",
+                                                      "rounds_ms", "bulk_ms", "n_tiles", "tile_cells", "pool_cells", "pool_max_passes")})
             return tot, h2d, d2h, nl
 
         for _ in range(min(args.warmup, 1)):
@@ -462,7 +467,7 @@ def main():
         t_e2e = allreduce(t_e2e, dist.ReduceOp.MAX if world > 1 else None)
         e2e = {"value": job_total / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": t_e2e / args.steps * 1e3, "row_blocks": n_blocks,
-               "host_buffers": "pinned f64 (what R's REAL() holds), day-major"}
+               "host_buffers": "pinned f64 (what R's REAL() holds), day-major", "block_stats_last_step": list(block_stats)}
         del h_f, h_out
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------

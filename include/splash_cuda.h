@@ -143,6 +143,7 @@ typedef struct splash_stats {
     double bulk_span_ms;    /* first bulk kernel start to last bulk kernel end (== their run time when nothing else runs, e.g. a resume call) */
     double d2h_ms;          /* device->host copies */
     double pool_wait_ms;    /* host wait for the straggler pool after every tile stream had drained */
+    double scatter_ms;      /* host time to move the pool's results into the caller's arrays */
     double gpu_ms;          /* first enqueue to last completion, CUDA events */
     double total_ms;        /* wall clock of the call */
     int64_t h2d_bytes;
@@ -189,6 +190,12 @@ int splash_point_run(splash_ctx* ctx, int64_t n_days, const int32_t* year, const
 
 /* Accounting of the last splash_grid_run / splash_point_run on this context. */
 int splash_last_stats(const splash_ctx* ctx, splash_stats* out);
+
+/* Diagnostic (used by tests/test_math_gpu.py, not by the R glue): apply one of the day step's
+ * transcendental functions to a host array on the device.  op: 0 exp, 1 log, 2 acos, 3 sin (hour
+ * angles, [0, pi]).  These are the library's own implementations (csrc/splash_math.cuh), which stand
+ * in for the libm calls of src/SPLASH.cpp, src/EVAP.cpp and src/SOLAR.cpp. */
+int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, double* y);
 
 #ifdef __cplusplus
 }

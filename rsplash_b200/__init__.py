@@ -14,3 +14,10 @@ def __getattr__(name):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)
+
+import os as _os
+
+# libsplash_cuda keeps ~20 CUDA streams busy per call (tiles, straggler pool, copies).  With CUDA's default
+# of 8 hardware work queues, streams share queues and kernels of one stream wait behind long-running
+# kernels of another.  The variable only counts before CUDA is initialised, so it is set on import.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

@@ -98,6 +98,7 @@ class SplashStats(C.Structure):
         ("bulk_span_ms", C.c_double),
         ("d2h_ms", C.c_double),
         ("pool_wait_ms", C.c_double),
+        ("scatter_ms", C.c_double),
         ("gpu_ms", C.c_double),
         ("total_ms", C.c_double),
         ("h2d_bytes", C.c_int64),

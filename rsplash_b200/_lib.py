@@ -13,7 +13,7 @@ from .build import LIB_PATH
 
 EXPORTS = (
     "splash_abi_version", "splash_ctx_create", "splash_ctx_destroy", "splash_last_error", "splash_count_months",
-    "splash_grid_run", "splash_point_run", "splash_last_stats",
+    "splash_grid_run", "splash_point_run", "splash_last_stats", "splash_debug_math",
 )
 
 _lib = None
@@ -54,6 +54,8 @@ def load() -> C.CDLL:
     lib.splash_point_run.restype = C.c_int
     lib.splash_last_stats.argtypes = [C.c_void_p, C.POINTER(_abi.SplashStats)]
     lib.splash_last_stats.restype = C.c_int
+    lib.splash_debug_math.argtypes = [C.c_void_p, C.c_int, C.c_int64, dp, dp]
+    lib.splash_debug_math.restype = C.c_int
     if lib.splash_abi_version() != _abi.SPLASH_ABI_VERSION:
         raise ImportError("libsplash_cuda ABI version mismatch; rebuild with `python -m rsplash_b200.build`")
     _lib = lib
@@ -95,6 +97,16 @@ class Context:
 
     def grid_run(self, cin: _abi.SplashGridIn, opts: _abi.SplashOpts, cout: _abi.SplashGridOut):
         self.check(self.lib.splash_grid_run(self.handle, C.byref(cin), C.byref(opts), C.byref(cout)))
+
+    def debug_math(self, op: str, x):
+        """exp / log / acos / sin of the day step evaluated on the device (diagnostic)."""
+        import numpy as np
+
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self.check(self.lib.splash_debug_math(self.handle, ("exp", "log", "acos", "sin").index(op), x.size,
+                                              x.ctypes.data_as(_abi.c_double_p), y.ctypes.data_as(_abi.c_double_p)))
+        return y
 
     def stats(self) -> dict:
         s = _abi.SplashStats()

@@ -32,8 +32,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "splash_model.cuh"
@@ -204,7 +206,8 @@ struct TileCtl {
     unsigned long long cycles;               // cells cut short by exact cycle detection
     unsigned long long pool_base, pool_end;  // this tile's range of the straggler pool
     unsigned long long pool_head;            // work-fetch cursor of the pool's daily-integration launch
-    unsigned long long spin_head;            // work-fetch cursor of the pool's spin-up launch
+    unsigned long long spin_head;            // work-fetch cursor of the pool's first spin-up stage
+    unsigned long long hard_n, hard_head;    // cells that exceeded the first stage's pass budget, and their cursor
     unsigned long long tail_head, tail_end;  // leftovers that did not fit the pool: finished in the tile
     unsigned long long max_chain;            // most year passes executed by one thread of a list-mode launch
 };
@@ -614,6 +617,7 @@ struct Pool {
     double* diag;        // [SPLASH_NDIAG][cap] (only the rows written by list mode are used)
     long long* cell;     // [cap] index of the cell in the caller's arrays
     double* table;       // [365][kDayPreDoubles][cap] forcing half of the cyclic spin-up year (k_pool_table)
+    int* hard;           // [cap] per tile range: pool cells handed to the second spin-up stage
     unsigned long long* count;  // entries handed out so far
     long long cap;
 };
@@ -697,16 +701,28 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
 // year passes with the reference's convergence test and exact cycle detection, the forcing half of every
 // day read from the table.  This is the longest sequential chain of the whole job (up to 1000 x 365 day
 // steps for a cell that never converges), so the loop body is kept to the state half only.
-__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool) {
+//
+// Two stages keep the lanes busy: most pool cells converge within a few dozen more passes, a few
+// percent run for hundreds.  Stage 1 gives every cell `budget` passes; the cells that exceed it are
+// appended to the tile's `hard` list and stage 2 runs only those, so that the warps which live for
+// seconds are few and full instead of many and nearly empty (they hold SM resources all the while).
+__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget) {
     extern __shared__ double s_cc[];
     StridedCC cc{s_cc + threadIdx.x, kListThreads};
     StridedCC snap{s_cc + (int64_t)NCC_DAY * kListThreads + threadIdx.x, kListThreads};
     unsigned long long spin_days = 0;
     int max_chain = 0;
     for (;;) {
-        const unsigned long long i = atomicAdd(&p.ctl->spin_head, 1ULL);
-        if (i >= p.ctl->pool_end) break;
-        const int c = (int)i;
+        int c;
+        if (stage == 1) {
+            const unsigned long long i = atomicAdd(&p.ctl->spin_head, 1ULL);
+            if (i >= p.ctl->pool_end) break;
+            c = (int)i;
+        } else {
+            const unsigned long long i = atomicAdd(&p.ctl->hard_head, 1ULL);
+            if (i >= p.ctl->hard_n) break;
+            c = pool.hard[p.ctl->pool_base + i];
+        }
         load_cc(p, c, cc);
         CellState st = load_state(p.w, c);
         CellState saved = st;
@@ -745,7 +761,19 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
                 d = 0;
                 ++passes;
                 ++chain;
+                if (stage == 1 && chain >= budget) break;  // st == E_k, the end of a pass: stage 2 resumes from it
             }
+        }
+        if (cont) {  // budget exhausted: park the cell for stage 2
+            store_state(p.w, c, st);
+            p.w.w1[c] = w1;
+            p.w.passes[c] = passes;
+            p.w.snap_pass[c] = snap_pass;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) p.w.snap[(int64_t)k * p.w.pitch + c] = snap(k);
+            const unsigned long long k2 = atomicAdd(&p.ctl->hard_n, 1ULL);
+            pool.hard[p.ctl->pool_base + k2] = c;
+            continue;
         }
         store_state(p.w, c, saved);  // the day-365 state is handed over, not the check day's
         p.w.passes[c] = passes;
@@ -783,6 +811,14 @@ __global__ void k_pool_scatter(Pool pool, long long n, long long n_out, double* 
 __global__ void k_finish_diag(const int* passes, double* diag, int64_t dpitch, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) diag[SPLASH_DIAG_SPIN_PASSES * dpitch + c] = (double)passes[c];
+}
+
+// diagnostic: the day step's transcendental functions applied to an array (splash_debug_math)
+__global__ void k_debug_math(int op, int64_t n, const double* x, double* y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    y[i] = op == 0 ? f_exp(v) : op == 1 ? f_log(v) : op == 2 ? f_acos(v) : f_sin(v);
 }
 
 __global__ void k_tile_begin(TileCtl* ctl, int n_cells) {  // (the control blocks are zeroed once per call)
@@ -869,12 +905,13 @@ struct DevBuf {
 };
 
 constexpr int kSlots = 3;         // forcing / output buffer sets in flight when they stream from / to the host
-constexpr int kRunStreams = 4;    // compute streams the tiles are dealt to
-constexpr int kPoolStreams = 16;  // streams of the straggler-pool launches
+constexpr int kRunStreams = 8;    // compute streams the tiles are dealt to
+constexpr int kPoolStreams = 8;   // streams of the straggler-pool launches
 #ifndef SPLASH_ROUNDS
 #define SPLASH_ROUNDS 20
 #endif
 constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before the leftovers go to the pool
+constexpr int kPoolStage1Passes = 32;   // pass budget of the pool's first spin-up stage
 static_assert(kRounds <= kMaxRounds, "kRounds");
 constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
 
@@ -897,6 +934,11 @@ struct splash_ctx {
     DevBuf forcing[kSlots][3], cellin[kSlots], outs[kSlots];
     std::vector<WorkSet> work;
     DevBuf dtab, dtab_spin, ctl, pool_mem;
+    // tuning knobs (environment overrides for experiments, read once at creation)
+    int n_run_streams = kRunStreams;      // SPLASH_RUN_STREAMS
+    int pool_stage1 = kPoolStage1Passes;  // SPLASH_POOL_STAGE1 (0 = single stage)
+    int two_pass = 1;                     // SPLASH_TWO_PASS
+    int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
 };
 
 namespace {
@@ -994,6 +1036,12 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     splash_ctx* ctx = nullptr;
     if (!out_ctx) return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_ctx_create: out_ctx is NULL");
     *out_ctx = nullptr;
+    // The call keeps ~25 streams busy (tiles, straggler pool, copies).  With the default of 8 hardware
+    // work queues several streams share one, and a tile's next kernel then waits behind another
+    // stream's seconds-long pool kernel (measured: tiles 4..7 started 2.6 s late).  Only effective if
+    // CUDA is not initialised in this process yet; hosts that initialise CUDA first (PyTorch) must
+    // export the variable themselves (rsplash_b200/__init__.py does).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)
@@ -1010,6 +1058,10 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     ctx = new splash_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("SPLASH_RUN_STREAMS")) ctx->n_run_streams = std::max(1, std::min(kRunStreams, atoi(v)));
+    if (const char* v = getenv("SPLASH_POOL_STAGE1")) ctx->pool_stage1 = std::max(0, atoi(v));
+    if (const char* v = getenv("SPLASH_TWO_PASS")) ctx->two_pass = atoi(v) != 0;
+    if (const char* v = getenv("SPLASH_ROUNDS_RT")) ctx->n_rounds = std::max(0, std::min(kRounds, atoi(v)));
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1072,6 +1124,22 @@ int splash_last_stats(const splash_ctx* ctx, splash_stats* out) {
     return SPLASH_OK;
 }
 
+int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, double* y) {
+    if (!ctx || !x || !y || n < 0 || op < 0 || op > 3) return SPLASH_ERR_BAD_ARG;
+    if (n == 0) return SPLASH_OK;
+    CU(cudaSetDevice(ctx->device));
+    double *dx = nullptr, *dy = nullptr;
+    CU(cudaMalloc(&dx, (size_t)n * 8));
+    CU(cudaMalloc(&dy, (size_t)n * 8));
+    CU(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    k_debug_math<<<(unsigned)((n + 255) / 256), 256>>>(op, n, dx, dy);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaFree(dx));
+    CU(cudaFree(dy));
+    return SPLASH_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -1098,6 +1166,7 @@ struct GridJob {
         cudaEvent_t h2d0, h2d1;                   // h2d stream: the tile's uploads
         cudaEvent_t k0, kf0, kf1, kr1, kb0, kb1;  // run stream: begin, k_spin_first begin/end, rounds end, bulk begin/end
         cudaEvent_t exported, run, d2h0, d2h1;    // stragglers exported; all tile kernels done; downloads
+        cudaEvent_t ps1, ps2, pm;                 // pool stream: spin stage 1 done, stage 2 done, daily integration done
     };
     std::vector<TileEv> ev;
     std::vector<RunParams> rps;
@@ -1105,7 +1174,7 @@ struct GridJob {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
     TileCtl* ctl(int64_t t) const { return (TileCtl*)ctx->ctl.p + t; }
-    cudaStream_t run_stream(int64_t t) const { return ctx->s_run[t % kRunStreams]; }
+    cudaStream_t run_stream(int64_t t) const { return ctx->s_run[t % ctx->n_run_streams]; }
     int work_of(int64_t t) const { return in_dev ? (int)t : (int)(t % kSlots); }
     int64_t cells_of(int64_t t) const { return std::min<int64_t>(tile, nc - t * tile); }
 
@@ -1121,11 +1190,11 @@ struct GridJob {
         for (auto& w : ctx->work) held += w.cc.cap + w.work_d.cap + w.work_i.cap + w.diag.cap;
         double budget = 0.80 * (double)(free_b + held);
 
-        // ---- straggler pool: a slice of the budget, ~1.5 % of the cells ---------------------------------
+        // ---- straggler pool: a slice of the budget, ~4 % of the cells -----------------------------------
         const double per_entry = 3.0 * (double)std::max<int64_t>(nd, 1) * fsz + (double)(NCC + 11 + SPLASH_NDIAG + 1) * 8.0 + 12.0 +
                                  (double)n_out_layers * (double)std::max<int64_t>(n_out, 1) * 8.0 +
                                  (double)kSpinYear * kDayPreDoubles * 8.0;
-        int64_t cap = std::min<int64_t>(std::max<int64_t>(nc / 64, 2048), 65536);
+        int64_t cap = std::min<int64_t>(std::max<int64_t>(nc / 24, 2048), 131072);
         cap = std::min<int64_t>(cap, (int64_t)(0.10 * budget / per_entry));
         cap = std::min<int64_t>(std::max<int64_t>(cap, 32), round_up(nc, 32));
         cap = round_up(cap, 32);
@@ -1145,6 +1214,7 @@ struct GridJob {
             const size_t o_dg = carve((size_t)SPLASH_NDIAG * cap * 8);
             const size_t o_cell = carve((size_t)cap * 8);
             const size_t o_tab = carve((size_t)kSpinYear * kDayPreDoubles * cap * 8);
+            const size_t o_hard = carve((size_t)cap * 4);
             const size_t o_cnt = carve(256);
             if (int rc = ensure(ctx, ctx->pool_mem, off)) return rc;
             char* b = (char*)ctx->pool_mem.p;
@@ -1165,6 +1235,7 @@ struct GridJob {
             pool.diag = (double*)(b + o_dg);
             pool.cell = (long long*)(b + o_cell);
             pool.table = (double*)(b + o_tab);
+            pool.hard = (int*)(b + o_hard);
             pool.count = (unsigned long long*)(b + o_cnt);
             pool.cap = cap;
             budget -= (double)off;
@@ -1221,7 +1292,7 @@ struct GridJob {
         CU(cudaStreamSynchronize(ctx->s_h2d));
         ev.resize((size_t)n_tiles);
         for (auto& t : ev) {
-            cudaEvent_t* timed[10] = {&t.h2d0, &t.h2d1, &t.k0, &t.kf0, &t.kf1, &t.kr1, &t.kb0, &t.kb1, &t.d2h0, &t.d2h1};
+            cudaEvent_t* timed[13] = {&t.h2d0, &t.h2d1, &t.k0, &t.kf0, &t.kf1, &t.kr1, &t.kb0, &t.kb1, &t.d2h0, &t.d2h1, &t.ps1, &t.ps2, &t.pm};
             for (auto* e : timed) CU(cudaEventCreate(e));
             CU(cudaEventCreateWithFlags(&t.exported, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&t.run, cudaEventDisableTiming));
@@ -1235,7 +1306,7 @@ struct GridJob {
 
     void release() {
         for (auto& t : ev) {
-            cudaEvent_t all[12] = {t.h2d0, t.h2d1, t.k0, t.kf0, t.kf1, t.kr1, t.kb0, t.kb1, t.d2h0, t.d2h1, t.exported, t.run};
+            cudaEvent_t all[15] = {t.h2d0, t.h2d1, t.k0, t.kf0, t.kf1, t.kr1, t.kb0, t.kb1, t.d2h0, t.d2h1, t.exported, t.run, t.ps1, t.ps2, t.pm};
             for (auto e : all)
                 if (e) cudaEventDestroy(e);
         }
@@ -1388,7 +1459,8 @@ struct GridJob {
         // ---- lock-step year passes; the list sizes stay on the device (grids are sized for the worst case,
         //      surplus CTAs exit at once) --------------------------------------------------------------------
         // a round can keep at most the cells of the previous one: after a few rounds a fraction of the grid suffices
-        for (int r = 0; r < kRounds; ++r) {
+        const int n_rounds = ctx->n_rounds;
+        for (int r = 0; r < n_rounds; ++r) {
             RunParams q = rp;
             q.round = r;
             k_spin_check<FT><<<grid_for(nct), kThreads, kSmemSpin, R>>>(q);
@@ -1398,8 +1470,8 @@ struct GridJob {
         }
         CU(cudaEventRecord(e.kr1, R));
         // ---- leftovers: into the pool (their own streams), or finished here if the pool is full -----------
-        k_pool_reserve<<<1, 1, 0, R>>>(rp.ctl, kRounds, pool.count, pool.cap);
-        k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, kRounds, (long long)c0);
+        k_pool_reserve<<<1, 1, 0, R>>>(rp.ctl, n_rounds, pool.count, pool.cap);
+        k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, n_rounds, (long long)c0);
         CU(cudaGetLastError());
         launches += 2;
         CU(cudaEventRecord(e.exported, R));
@@ -1424,16 +1496,21 @@ struct GridJob {
             pp.q_list = nullptr;
             // forcing half of the cyclic year once, the spin-up chain on the state half, then the daily integration
             k_pool_table<FT><<<(unsigned)(ctx->sm_count * 2), 128, 0, Q>>>(pp, pool);
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool);
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1,
+                                                                                     ctx->pool_stage1 > 0 ? ctx->pool_stage1 : (1 << 30));
+            CU(cudaEventRecord(e.ps1, Q));
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, 0);
+            CU(cudaEventRecord(e.ps2, Q));
             launch_list<FT>(pp, monthly, ctx->sm_count * 2, Q);
+            CU(cudaEventRecord(e.pm, Q));
             CU(cudaGetLastError());
-            launches += 3;
+            launches += 4;
         }
         {
             RunParams tp = rp;
             tp.q_head = &rp.ctl->tail_head;
             tp.q_end = &rp.ctl->tail_end;
-            tp.q_list = rp.lists[kRounds & 1];
+            tp.q_list = n_rounds ? rp.lists[n_rounds & 1] : nullptr;
             launch_list<FT>(tp, monthly, ctx->sm_count * 2, R);
             CU(cudaGetLastError());
             ++launches;
@@ -1505,10 +1582,21 @@ struct GridJob {
             CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.out[k], (size_t)pool.cap * 8, (size_t)n_pool * 8, (size_t)n_out,
                             cudaMemcpyDeviceToHost));
             ctx->stats.d2h_bytes += n_pool * n_out * 8;
-            for (int64_t r = 0; r < n_out; ++r) {
-                double* dst = out_ptr[k] + r * ostride;
-                const double* src = buf.data() + r * n_pool;
-                for (int64_t j = 0; j < n_pool; ++j) dst[cell[(size_t)j]] = src[j];
+            // rows are independent: a few host threads hide the cache misses of the scattered stores
+            const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), n_out}));
+            auto rows = [&](int64_t r0, int64_t r1) {
+                for (int64_t r = r0; r < r1; ++r) {
+                    double* dst = out_ptr[k] + r * ostride;
+                    const double* src = buf.data() + r * n_pool;
+                    for (int64_t j = 0; j < n_pool; ++j) dst[cell[(size_t)j]] = src[j];
+                }
+            };
+            if (n_thr == 1 || n_pool * n_out < (1 << 16)) {
+                rows(0, n_out);
+            } else {
+                std::vector<std::thread> th;
+                for (int i = 0; i < n_thr; ++i) th.emplace_back(rows, n_out * i / n_thr, n_out * (i + 1) / n_thr);
+                for (auto& t : th) t.join();
             }
         }
         if (out->state_final) {
@@ -1530,8 +1618,8 @@ struct GridJob {
         if (int rc = plan()) return rc;
         if (int rc = allocate()) return rc;
         CU(cudaEventRecord(ev_begin, ctx->s_h2d));
-        for (auto s : ctx->s_run) CU(cudaStreamWaitEvent(s, ev_begin, 0));
-        if (in_dev && out_dev) {
+        for (auto s : ctx->s_run) CU(cudaStreamWaitEvent(s, ev_begin, 0));  // (idle streams included: harmless)
+        if (in_dev && out_dev && ctx->two_pass) {
             // resident data: every tile's spin-up first, so that the stragglers (up to 1000 sequential year
             // passes) start as early as possible and run beside the daily integration of all tiles
             for (int64_t t = 0; t < n_tiles; ++t) {
@@ -1557,7 +1645,9 @@ struct GridJob {
         unsigned long long pool_count = 0;
         CU(cudaMemcpy(&pool_count, pool.count, 8, cudaMemcpyDeviceToHost));
         const int64_t n_pool = (int64_t)std::min<unsigned long long>(pool_count, (unsigned long long)pool.cap);
+        const auto t_sc0 = std::chrono::steady_clock::now();
         if (int rc = scatter_pool(n_pool)) return rc;
+        ctx->stats.scatter_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sc0).count();
         CU(cudaEventRecord(ev_end, ctx->s_d2h));
         CU(cudaEventSynchronize(ev_end));
 
@@ -1581,6 +1671,21 @@ struct GridJob {
             if (cudaEventElapsedTime(&ms, e.kf1, e.kr1) == cudaSuccess) st.rounds_ms += ms;
             if (cudaEventElapsedTime(&ms, e.kb0, e.kb1) == cudaSuccess) st.bulk_ms += ms;
             if (cudaEventElapsedTime(&ms, e.d2h0, e.d2h1) == cudaSuccess) st.d2h_ms += ms;
+        }
+        if (getenv("SPLASH_TRACE")) {  // per-tile timeline, ms since the first enqueue
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const TileEv& e = ev[(size_t)t];
+                const TileCtl& c = h_ctl[(size_t)t];
+                auto at = [&](cudaEvent_t x) {
+                    float m = -1;
+                    return cudaEventElapsedTime(&m, ev_begin, x) == cudaSuccess ? (double)m : -1.0;
+                };
+                fprintf(stderr,
+                        "[splash trace] tile %2lld: start %7.1f first %7.1f..%7.1f rounds_end %7.1f bulk %7.1f..%7.1f | pool n=%llu hard=%llu "
+                        "stage1_end %7.1f stage2_end %7.1f main_end %7.1f max_chain %llu\n",
+                        (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n,
+                        opts.skip_spinup ? -1.0 : at(e.ps1), opts.skip_spinup ? -1.0 : at(e.ps2), opts.skip_spinup ? -1.0 : at(e.pm), c.max_chain);
+            }
         }
         float ms = 0;
         for (int64_t t0 = 0; t0 < std::min<int64_t>(kRunStreams, n_tiles); ++t0)

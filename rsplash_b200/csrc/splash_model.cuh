@@ -46,6 +46,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "splash_math.cuh"
+
 namespace splash {
 
 // ------------------------------------------------------------------------------------------------
@@ -123,12 +125,16 @@ struct DayOut {
 };
 
 #if SPLASH_L1_RECIP
+#define SPLASH_FDIV(a, b) fm::fdiv((a), (b))       // a/b to ~1.5 ulp, IEEE behaviour for 0/inf/NaN denominators
+#define SPLASH_DIVC(a, c) ((a) * (1.0 / (c)))      // division by a compile-time constant
 #define SPLASH_TO_DEG(x) ((x) * (180.0 / kPI))
 #define SPLASH_DIV_D1000(x) ((x) * cc(C_INV_D1000))
 #define SPLASH_DIV_DTH(x) ((x) * cc(C_INV_DTH))
 #define SPLASH_DIV_TAU_B(x) ((x) * cc(C_INV_TAU_B))
 #define SPLASH_DIV_1000(x) ((x) * 1e-3)
 #else
+#define SPLASH_FDIV(a, b) ((a) / (b))
+#define SPLASH_DIVC(a, c) ((a) / (c))
 #define SPLASH_TO_DEG(x) ((x) / kpir)
 #define SPLASH_DIV_D1000(x) ((x) / cc(C_D1000))
 #define SPLASH_DIV_DTH(x) ((x) / cc(C_DTH))
@@ -139,10 +145,17 @@ struct DayOut {
 // One shared copy of each transcendental instead of ~25 inlined expansions: the day step is a
 // single long loop body and its code size, not its arithmetic, was the first bottleneck (ncu:
 // 48 % of warp-stall samples were `no_instruction` with a 91 KB kernel, profiles/README.md).
+#if SPLASH_LEVEL >= 1 && !defined(SPLASH_LIBDEVICE_MATH)
+using fm::f_acos;  // splash_math.cuh: coefficients in __constant__ memory instead of 64-bit immediates
+using fm::f_exp;
+using fm::f_log;
+using fm::f_sin;
+#else
 __device__ __noinline__ double f_exp(double x) { return exp(x); }
 __device__ __noinline__ double f_log(double x) { return log(x); }
 __device__ __noinline__ double f_acos(double x) { return acos(x); }
 __device__ __noinline__ double f_sin(double x) { return sin(x); }
+#endif
 
 // std::max / std::min semantics of the reference (NaN in the first argument wins, SURVEY B-1)
 __device__ __forceinline__ double cxx_max(double a, double b) { return (a < b) ? b : a; }
@@ -228,10 +241,12 @@ __device__ __forceinline__ DensityPoly density_poly(double tc) {
 }
 
 // pressure part of EVAP::density_h2o, src/EVAP.cpp:381-388 (pbar = 1e-5 * p)
+// kExact: the IEEE division, for the value that is narrowed to float in the viscosity routine.
+template <bool kExact = false>
 __device__ __forceinline__ double density_at(const DensityPoly& q, double pbar) {
     const double num = (q.ko + q.ca * pbar + q.cb * (pbar * pbar));
     double pw = num;
-    pw /= (num - pbar);
+    pw = kExact ? pw / (num - pbar) : SPLASH_FDIV(pw, num - pbar);
     pw *= (1.0e3) * q.po;
     return pw;
 }
@@ -319,7 +334,7 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
     const double theta_i = SPLASH_DIV_D1000(sm);
     const double x = SPLASH_DIV_DTH(theta_i - cc(C_THR));
     const double a = cc(C_ILAM) * f_log(x);  // log shared by x^(1/lambda) and (x^(1/lambda))^(3 lambda + 1)
-    const double psi_m = bub / f_exp(a);
+    const double psi_m = SPLASH_FDIV(bub, f_exp(a));
     double wtd = SPLASH_DIV_1000(bub - psi_m);
     if (wtd < 0.0 || isnan(wtd)) {
         wtd = 0.01;
@@ -329,7 +344,7 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
     r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
     const double r1 = f_exp(e3 * a);  // (bub/psi_m)^e3 with bub/psi_m == x^(1/lambda)
     // second power: its base is 1 up to rounding noise unless wtd was clamped; first-order expansion there
-    const double q = bub / (psi_m + (wtd * 1000.0));
+    const double q = SPLASH_FDIV(bub, psi_m + (wtd * 1000.0));
     const double qm1 = q - 1.0;
     const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : f_exp(e3 * f_log(q));
     double t_uns = (ksat_visc * bub / e3) * (r1 - r2);
@@ -356,7 +371,7 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
 // snowfall_prob's exponent, R/splash.point.R:576
 template <class CC>
 __device__ __forceinline__ double snow_prob(const CC& cc, double tc) {
-    return 1 / (1 + f_exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
+    return SPLASH_FDIV(1.0, 1 + f_exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,7 +415,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     } else if (p_snow >= 0.5) {
         const double Tt = cc(C_TT);
         const double Ttm = Tt + (Tt * mt.s1[dt.month]);
-        const double x = (tc - Ttm) / (mt.trm14[dt.month]);
+        const double x = SPLASH_FDIV(tc - Ttm, mt.trm14[dt.month]);
         double frain;
         if (tc <= Ttm) {
             frain = 5 * (x * x * x) + 6.76 * (x * x) + 3.19 * x + 0.5;
@@ -424,14 +439,14 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     const double d = b * b + c * c - a * a;
     double sinfirst;
     if (d < 0) {
-        sinfirst = (a * c) / (b * b + c * c);
+        sinfirst = SPLASH_FDIV(a * c, b * b + c * c);
     } else {
-        sinfirst = (a * c + b * sqrt(d)) / (b * b + c * c);
+        sinfirst = SPLASH_FDIV(a * c + b * sqrt(d), b * b + c * c);
     }
     const double ru = -1 * a + c * sinfirst;
     const double rv = b;
     double hs;
-    const double ruv = ru / rv;
+    const double ruv = SPLASH_FDIV(ru, rv);
     if (ruv >= 1.0) {
         hs = 180.0;
     } else if (ruv <= -1.0) {
@@ -450,7 +465,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     if (isnan(ra_d) || r_in == 0 || ra_d < r_in) {
         tau = tau_o;
     } else {
-        tau = r_in / (ra_d);
+        tau = SPLASH_FDIV(r_in, ra_d);
     }
 #if SPLASH_L1_POW
     double sf = f_exp((1 / 0.7410) * f_log(SPLASH_DIV_TAU_B(tau - cc(C_TAU_A))));
@@ -476,17 +491,17 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
 
     // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:100-145 --------------------------------------------
     const double patm = cc(C_PATM);
-    double s = f_exp((tc * 17.269) / (tc + 237.3));  // sat_slope, :299-301
-    s /= ((tc + 237.3) * (tc + 237.3));
+    double s = f_exp(SPLASH_FDIV(tc * 17.269, tc + 237.3));  // sat_slope, :299-301
+    s = SPLASH_FDIV(s, (tc + 237.3) * (tc + 237.3));
     s *= (17.269) * (237.3) * (610.78);
-    double lv = (tc + 273.15) / (tc + 273.15 - 33.91);  // enthalpy_vap, :313-315
+    double lv = SPLASH_FDIV(tc + 273.15, tc + 273.15 - 33.91);  // enthalpy_vap, :313-315
     lv = lv * lv;
     lv *= 1.91846e6;
     const DensityPoly qd = density_poly(tc);
     const double pw = density_at(qd, cc(C_PBAR));
     const double cp = specific_heat(tc);
-    const double g = (kMa * cp * patm) / (kMv * lv);  // psychro, :486
-    const double econ = s / (lv * pw * (s + g));
+    const double g = SPLASH_FDIV(kMa * cp * patm, kMv * lv);  // psychro, :486
+    const double econ = SPLASH_FDIV(s, lv * pw * (s + g));
     // viscosity at tw = max(tc, 0) narrowed to float, :100-105,120,413
     double visc;
     if (tc < 0.0) {
@@ -495,9 +510,9 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         const float tcf = (float)tc;
         double rho_d;
         if ((double)tcf == tc) {
-            rho_d = density_at(qd, cc(C_PBARF));  // same temperature polynomials, float-rounded pressure
+            rho_d = density_at<true>(qd, cc(C_PBARF));  // same temperature polynomials, float-rounded pressure
         } else {
-            rho_d = density_at(density_poly((double)tcf), cc(C_PBARF));
+            rho_d = density_at<true>(density_poly((double)tcf), cc(C_PBARF));
         }
         visc = viscosity_h2o(tcf, rho_d);
     }
@@ -505,9 +520,9 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.g = g;
     q.econ = econ;
     q.pw = pw;
-    q.eet_k = (1.0e3) * (s / (lv * pw * (s + 0.24 * g)));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
+    q.eet_k = (1.0e3) * SPLASH_FDIV(s, lv * pw * (s + 0.24 * g));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
     q.rx = (3.6e6) * econ;
-    q.ksat_visc = cc(C_INTPERM) * ((pw * kG) / visc) * 3.6;  // SPLASH.cpp:1260
+    q.ksat_visc = cc(C_INTPERM) * SPLASH_FDIV(pw * kG, visc) * 3.6;  // SPLASH.cpp:1260
 }
 
 template <class CC>
@@ -545,17 +560,17 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:208-255 ------------------------------------------
     const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
     const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * f_exp(-0.895189 * nd));
-    const double sfc = snow / (140.0 + snow);
+    const double sfc = SPLASH_FDIV(snow, 140.0 + snow);
     const double alb_v = kalb_sw - 0.17 * sw;
     const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
     double rw;
     if (q.rw_dark != 0.0) {
         rw = (1.0 - alb) * q.tau * q.dr * kGsc;
     } else {
-        rw = (1.0 - alb) * (q.r_in) / q.rw_den;
+        rw = SPLASH_FDIV((1.0 - alb) * (q.r_in), q.rw_den);
     }
     double hn;
-    const double qn = (rnl - rw * ru) / (rw * rv);
+    const double qn = SPLASH_FDIV(rnl - rw * ru, rw * rv);
     if (qn >= 1.0) {
         hn = 0;
     } else if (qn <= -1.0) {
@@ -577,13 +592,13 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
     const double eet_d = q.eet_k * rn_d;
     const double pet_max = rx * ((rw * (ru + rv)) - rnl);
-    const double B_r = g / (sw * s);
-    const double EF = 1 / (B_r + 1.0);
+    const double B_r = SPLASH_FDIV(g, sw * s);
+    const double EF = SPLASH_FDIV(1.0, B_r + 1.0);
     double swp = pet_max * EF;
     if (swp < 0.0 || isnan(swp)) {
         swp = 0.0;
     }
-    const double cos_hi = swp / (rw * rv * rx) + rnl / (rw * rv) - q.ruv;  // ru/rv: same operands as in day_forcing
+    const double cos_hi = SPLASH_FDIV(swp, rw * rv * rx) + SPLASH_FDIV(rnl, rw * rv) - q.ruv;  // ru/rv: same operands as in day_forcing
     double hi;
     if (cos_hi >= 1.0) {
         hi = 0.0;
@@ -595,14 +610,14 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     }
     double snowmelt_tot;
     if (tc >= 3.0) {
-        snowmelt_tot = cxx_min(snow, (rn_d / (pw * kkfus)) * 1000.0);
+        snowmelt_tot = cxx_min(snow, SPLASH_FDIV(rn_d, pw * kkfus) * 1000.0);
     } else {
         snowmelt_tot = 0.0;
     }
-    double melt_enrg = (snowmelt_tot / 1000) * pw * kkfus;
+    double melt_enrg = SPLASH_DIVC(snowmelt_tot, 1000.0) * pw * kkfus;
     const double AE = rn_d - melt_enrg;
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
-    melt_enrg += ((sublimation / 1000.0) / econ);
+    melt_enrg += SPLASH_FDIV(SPLASH_DIVC(sublimation, 1000.0), econ);
     double aet_d = swp * hi * kpir;
     aet_d += rx * rw * rv * (sin_hn - f_sin(hi * kpir));
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
@@ -644,7 +659,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     double infi;
     {
         const double P = inflow;
-        const double r = P / 6.0;
+        const double r = SPLASH_DIVC(P, 6.0);
         const double h_f = cc(C_HF);
         const double delta_theta = (theta_s - surf_moist);
         double I = 0.0;
@@ -654,12 +669,12 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
             if (delta_theta <= 0.0) {
                 I = Ksat_visc * 6.0;
             } else {
-                double tp = (Ksat_visc * delta_theta * -1.0 * h_f) / (r * (r - Ksat_visc));
+                double tp = SPLASH_FDIV(Ksat_visc * delta_theta * -1.0 * h_f, r * (r - Ksat_visc));
                 if (tp <= 0.0 || isnan(tp)) {
                     tp = 0.01;
                 }
                 const double tp_s = tp / cc(C_COS2_S);
-                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * f_log(1 - (r * tp_s / (h_f * delta_theta)))));
+                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * f_log(1 - SPLASH_FDIV(r * tp_s, h_f * delta_theta))));
             }
         }
         if (I > P) {
@@ -681,14 +696,14 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double Kunsat = Ksat_visc * pow((theta_m / theta_s), cc(C_KUEXP));
 #endif
     const double hyd_grad_in = cc(C_TAN_S);
-    const double hyd_grad_z = (infi / (Ksat_visc * 24)) - 1.0;
+    const double hyd_grad_z = SPLASH_FDIV(infi, Ksat_visc * 24) - 1.0;
     const double hyd_grad_out = sqrt((hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in));
 
     // ---- 5.2.1 recession constant, :1303-1326 ------------------------------------------------------
     const double kbe3 = (Ksat_visc * cc(C_BUB) / cc(C_E3));
     const double T_q0 = kbe3 * cc(C_BRQ0);
     const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
-    const double Q_qs = (hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS) / 1000.0);
+    const double Q_qs = SPLASH_DIVC(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS), 1000.0);
 #if SPLASH_L1_RECIP
     const double Kb = f_exp((Q_q0 - Q_qs) * cc(C_INV_DENKB));
 #else
@@ -697,7 +712,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     // ---- 5.2.2 drainage at Wmax, :1346-1360 --------------------------------------------------------
     const double To_uns = kbe3 * cc(C_BRW);
     const double Qo_uns = To_uns * cc(C_CW);
-    const double Qo_sat = Ksat_visc * 24.0 * cc(C_ACSW) / 1000.0;
+    const double Qo_sat = SPLASH_DIVC(Ksat_visc * 24.0 * cc(C_ACSW), 1000.0);
     const double Qt = (Qo_sat + Qo_uns) * hyd_grad_out;
     // ---- 5.2.3 upslope input of the previous day, :1365-1372 ---------------------------------------
     double q_in_o = 0.0;
@@ -740,7 +755,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         }
         T = (T_sat + T_uns) * hyd_grad_out;
     }
-    const double Q = (T * Ai) / 1000;
+    const double Q = SPLASH_DIVC(T * Ai, 1000.0);
     // ---- 5.7 same-day upslope input, :1465-1483 ----------------------------------------------------
     double t_drain = 0.0;
     double q_in_f = 0.0;
@@ -748,7 +763,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     if ((R > 0.0) && (sm > cc(C_WMAX))) {
         const double lkb = f_log(Kb);
         const double Au = cc(C_AU);
-        t_drain = -1.0 * f_log(1.0 - (lkb * (Au * R / Q))) / lkb;
+        t_drain = SPLASH_FDIV(-1.0 * f_log(1.0 - (lkb * SPLASH_FDIV(Au * R, Q))), lkb);
         q_in_f = SPLASH_DIV_AI(Qt - Au * R * lkb);
     }
     if (q_in_f < 0.0 || isnan(q_in_f)) {
@@ -792,7 +807,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     o.aet = aet_d;
     o.cond = cn;
     o.bflow = T;
-    o.netr = rn_d / 1e6;
+    o.netr = SPLASH_DIVC(rn_d, 1e6);
 #undef SPLASH_DIV_AI
 }
 
@@ -845,18 +860,18 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     const double dp = 1 / ((fOM / 1.3) + ((1 - fOM) / 2.65));
     double bd = in.bd;
     if (isnan(bd)) {
-        bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - f_exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
+        bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
     }
     if (bd < 0.81) bd = 0.81;
     double sat = 1 - (bd / dp);
     const double sq_clay = sqrt(fclay);  // fclay^0.5
     double fc = (sat / bd) * (0.4760944 + (0.9402962 - 0.4760944) * sq_clay) *
-                f_exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
+                exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
     const double wp_Ball = fc * (0.2018522 + (0.7809203 - 0.2018522) * sq_clay);
     double wp = -2.464e-05 * in.sand + 3.650e-03 * in.clay + 8.680e-03 * in.om + 9.393e-03 * bd;
     if (!isnan(wp) && wp >= fc) wp = wp_Ball;
-    const double coef_B = (f_log(1500.0) - f_log(33.0)) / (f_log(fc) - f_log(wp));
-    const double coef_A = f_exp(f_log(33.0) + coef_B * f_log(fc));
+    const double coef_B = (log(1500.0) - log(33.0)) / (log(fc) - log(wp));
+    const double coef_A = exp(log(33.0) + coef_B * log(fc));
     const double coef_lambda = 1 / coef_B;
     const double coeff_c = 1000.0 / (997 * 9.80665);
     const double theta_c = pow((coeff_c * coef_A / 2.0), (1 / (1 + coef_B)));
@@ -865,7 +880,7 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     sat = sat * (1 - fgravel);
     fc = fc * (1 - fgravel);
     wp = wp * (1 - fgravel);
-    const double ksat = 857.48454 / (1 + f_exp(-2.70927 * fsand + 3.62264 * bd + 7.33398 * fclay + -8.11795 * (sat - fc) +
+    const double ksat = 857.48454 / (1 + exp(-2.70927 * fsand + 3.62264 * bd + 7.33398 * fclay + -8.11795 * (sat - fc) +
                                             18.75552 * fOM + 1.03319 * coef_lambda));
     const double m33i = 0.278 * fsand + 0.034 * fclay + 0.022 * fOM - 0.018 * (fsand * fOM) - 0.027 * (fclay * fOM) -
                         0.584 * (fsand * fclay) + 0.078;
@@ -902,12 +917,12 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     cc(C_LAT_K) = fabs(in.lat) * 0.0110592101;
     const double asp = in.asp - 180;  // R/splash.point.R:131
     cc(C_COS_LAT) = cos(in.lat * kpir);
-    cc(C_SIN_LAT) = f_sin(in.lat * kpir);
-    cc(C_SIN_S) = f_sin(in.slop * kpir);
+    cc(C_SIN_LAT) = sin(in.lat * kpir);
+    cc(C_SIN_S) = sin(in.slop * kpir);
     const double cos_s = cos(in.slop * kpir);
     cc(C_COS_S) = cos_s;
     cc(C_COS_A) = cos(asp * kpir);
-    cc(C_SIN_A) = f_sin(asp * kpir);
+    cc(C_SIN_A) = sin(asp * kpir);
     cc(C_TAN_S) = tan(in.slop * kpir);
     cc(C_COS2_S) = cos_s * cos_s;
     // ---- atmosphere: SOLAR.cpp:170,197; EVAP.cpp:331-334 -------------------------------------------
@@ -923,7 +938,7 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     cc(C_PBAR) = (1.0e-5) * patm;
     const double pbarf = (1.0e-5) * (double)(float)patm;
     cc(C_PBARF) = pbarf;
-    cc(C_VISC0) = viscosity_h2o(0.0f, density_at(density_poly(0.0), pbarf));
+    cc(C_VISC0) = viscosity_h2o(0.0f, density_at<true>(density_poly(0.0), pbarf));
     // ---- soil column: SPLASH.cpp:971-1029 ----------------------------------------------------------
     const double d1000 = depth * 1000.0;
     const double theta_s = SAT / d1000;
@@ -962,7 +977,7 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     cc(C_BUB) = bub;
     cc(C_BP10) = bub / 10;
     const double KG_o = 1000.0 / (997 * kG);
-    const double coeff_A = f_exp(f_log(33.0) + (1.0 / lambda) * f_log(theta_fc));
+    const double coeff_A = exp(log(33.0) + (1.0 / lambda) * log(theta_fc));
     const double Wmax = pow((coeff_A * KG_o / (depth)), (1.0 / ((1 / lambda) + 1.0))) * (depth * 1000.0);
     cc(C_WMAX) = Wmax;
     cc(C_WMR) = (Wmax - RES);
