@@ -207,7 +207,7 @@ struct TileCtl {
     unsigned long long pool_base, pool_end;  // this tile's range of the straggler pool
     unsigned long long pool_head;            // work-fetch cursor of the pool's daily-integration launch
     unsigned long long spin_head;            // work-fetch cursor of the pool's first spin-up stage
-    unsigned long long hard_n, hard_head;    // cells that exceeded the first stage's pass budget, and their cursor
+    unsigned long long hard_n[4], hard_head[4];  // hard_n[s]: cells that exceeded stage s's pass budget; cursor of the stage that reads them
     unsigned long long tail_head, tail_end;  // leftovers that did not fit the pool: finished in the tile
     unsigned long long max_chain;            // most year passes executed by one thread of a list-mode launch
 };
@@ -617,7 +617,7 @@ struct Pool {
     double* diag;        // [SPLASH_NDIAG][cap] (only the rows written by list mode are used)
     long long* cell;     // [cap] index of the cell in the caller's arrays
     double* table;       // [365][kDayPreDoubles][cap] forcing half of the cyclic spin-up year (k_pool_table)
-    int* hard;           // [cap] per tile range: pool cells handed to the second spin-up stage
+    int* hard[2];        // [cap] each, per tile range, ping-pong: pool cells handed from one spin-up stage to the next
     unsigned long long* count;  // entries handed out so far
     long long cap;
 };
@@ -702,12 +702,16 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
 // day read from the table.  This is the longest sequential chain of the whole job (up to 1000 x 365 day
 // steps for a cell that never converges), so the loop body is kept to the state half only.
 //
-// Two stages keep the lanes busy: most pool cells converge within a few dozen more passes, a few
-// percent run for hundreds.  Stage 1 gives every cell `budget` passes; the cells that exceed it are
-// appended to the tile's `hard` list and stage 2 runs only those, so that the warps which live for
-// seconds are few and full instead of many and nearly empty (they hold SM resources all the while).
-__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget) {
+// Stages keep the lanes busy: most pool cells converge within a few dozen more passes, a few percent
+// run for hundreds.  Stage s gives every cell it receives `budget` passes; the cells that exceed it
+// are appended to the tile's next `hard` list and stage s+1 runs only those, so that the warps which
+// live for seconds are few and full instead of many and nearly empty (they hold SM resources all the
+// while).  The last stage is launched with enough shared memory per CTA that no 512-thread CTA of the
+// uniform kernels fits beside it: its warps (at most four per SM) own their SM and run the chain at
+// its uncontended latency, roughly half the time per day step of a warp squeezed in beside 16 others.
+__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget, int lanes) {
     extern __shared__ double s_cc[];
+    if ((int)threadIdx.x >= lanes) return;  // last stage: fewer cells per warp = fewer divergent paths per day step
     StridedCC cc{s_cc + threadIdx.x, kListThreads};
     StridedCC snap{s_cc + (int64_t)NCC_DAY * kListThreads + threadIdx.x, kListThreads};
     unsigned long long spin_days = 0;
@@ -719,9 +723,9 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
             if (i >= p.ctl->pool_end) break;
             c = (int)i;
         } else {
-            const unsigned long long i = atomicAdd(&p.ctl->hard_head, 1ULL);
-            if (i >= p.ctl->hard_n) break;
-            c = pool.hard[p.ctl->pool_base + i];
+            const unsigned long long i = atomicAdd(&p.ctl->hard_head[stage - 1], 1ULL);
+            if (i >= p.ctl->hard_n[stage - 1]) break;
+            c = pool.hard[(stage - 1) & 1][p.ctl->pool_base + i];
         }
         load_cc(p, c, cc);
         CellState st = load_state(p.w, c);
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
                 d = 0;
                 ++passes;
                 ++chain;
-                if (stage == 1 && chain >= budget) break;  // st == E_k, the end of a pass: stage 2 resumes from it
+                if (chain >= budget) break;  // st == E_k, the end of a pass: the next stage resumes from it
             }
         }
         if (cont) {  // budget exhausted: park the cell for stage 2
@@ -771,8 +775,8 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
             p.w.snap_pass[c] = snap_pass;
 #pragma unroll
             for (int k = 0; k < 5; ++k) p.w.snap[(int64_t)k * p.w.pitch + c] = snap(k);
-            const unsigned long long k2 = atomicAdd(&p.ctl->hard_n, 1ULL);
-            pool.hard[p.ctl->pool_base + k2] = c;
+            const unsigned long long k2 = atomicAdd(&p.ctl->hard_n[stage], 1ULL);
+            pool.hard[stage & 1][p.ctl->pool_base + k2] = c;
             continue;
         }
         store_state(p.w, c, saved);  // the day-365 state is handed over, not the check day's
@@ -906,12 +910,14 @@ struct DevBuf {
 
 constexpr int kSlots = 3;         // forcing / output buffer sets in flight when they stream from / to the host
 constexpr int kRunStreams = 8;    // compute streams the tiles are dealt to
-constexpr int kPoolStreams = 8;   // streams of the straggler-pool launches
+constexpr int kPoolStreams = 16;  // streams of the straggler-pool launches: a tile's pool work must not queue behind
+                                  // another tile's seconds-long chain, so calls are cut into at most 16 tiles when possible
 #ifndef SPLASH_ROUNDS
 #define SPLASH_ROUNDS 20
 #endif
 constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before the leftovers go to the pool
-constexpr int kPoolStage1Passes = 32;   // pass budget of the pool's first spin-up stage
+constexpr int kPoolStage1Passes = 8;    // pass budget of the pool's first spin-up stage
+constexpr int kPoolStage2Passes = 64;   // ... and of the second; the third runs to the reference's pass limit
 static_assert(kRounds <= kMaxRounds, "kRounds");
 constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
 
@@ -937,6 +943,9 @@ struct splash_ctx {
     // tuning knobs (environment overrides for experiments, read once at creation)
     int n_run_streams = kRunStreams;      // SPLASH_RUN_STREAMS
     int pool_stage1 = kPoolStage1Passes;  // SPLASH_POOL_STAGE1 (0 = single stage)
+    int pool_stage2 = kPoolStage2Passes;  // SPLASH_POOL_STAGE2
+    int pool_excl_smem = 0;               // dynamic shared memory of a last-stage CTA (SPLASH_POOL_EXCL=0: no exclusivity)
+    int pool_last_lanes = 8, pool_last_ctas = 192;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
 };
@@ -996,7 +1005,7 @@ cudaError_t prepare_kernels() {
     if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
     if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
-    if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
+    if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
     return cudaSuccess;
 }
 
@@ -1061,6 +1070,17 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     if (const char* v = getenv("SPLASH_RUN_STREAMS")) ctx->n_run_streams = std::max(1, std::min(kRunStreams, atoi(v)));
     if (const char* v = getenv("SPLASH_POOL_STAGE1")) ctx->pool_stage1 = std::max(0, atoi(v));
     if (const char* v = getenv("SPLASH_TWO_PASS")) ctx->two_pass = atoi(v) != 0;
+    if (const char* v = getenv("SPLASH_POOL_STAGE2")) ctx->pool_stage2 = std::max(1, atoi(v));
+    if (const char* v = getenv("SPLASH_POOL_LANES")) ctx->pool_last_lanes = std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("SPLASH_POOL_CTAS")) ctx->pool_last_ctas = std::max(1, atoi(v));
+    {
+        // a quarter of the SM's shared memory per last-stage CTA: four of them fill an SM, and none fits
+        // beside a uniform CTA (kSmemUniform)
+        const char* v = getenv("SPLASH_POOL_EXCL");
+        const bool excl = v && atoi(v) != 0;  // off by default: measured no gain (the chain is latency-, not contention-bound)
+        const int quarter = ((int)prop.sharedMemPerMultiprocessor - 4 * 1024) / 4 / 1024 * 1024;
+        ctx->pool_excl_smem = excl ? std::max<int>((int)kSmemList, std::min<int>(quarter, (int)prop.sharedMemPerBlockOptin)) : (int)kSmemList;
+    }
     if (const char* v = getenv("SPLASH_ROUNDS_RT")) ctx->n_rounds = std::max(0, std::min(kRounds, atoi(v)));
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
@@ -1214,7 +1234,7 @@ struct GridJob {
             const size_t o_dg = carve((size_t)SPLASH_NDIAG * cap * 8);
             const size_t o_cell = carve((size_t)cap * 8);
             const size_t o_tab = carve((size_t)kSpinYear * kDayPreDoubles * cap * 8);
-            const size_t o_hard = carve((size_t)cap * 4);
+            const size_t o_hard = carve((size_t)cap * 4 * 2);
             const size_t o_cnt = carve(256);
             if (int rc = ensure(ctx, ctx->pool_mem, off)) return rc;
             char* b = (char*)ctx->pool_mem.p;
@@ -1235,7 +1255,8 @@ struct GridJob {
             pool.diag = (double*)(b + o_dg);
             pool.cell = (long long*)(b + o_cell);
             pool.table = (double*)(b + o_tab);
-            pool.hard = (int*)(b + o_hard);
+            pool.hard[0] = (int*)(b + o_hard);
+            pool.hard[1] = pool.hard[0] + cap;
             pool.count = (unsigned long long*)(b + o_cnt);
             pool.cap = cap;
             budget -= (double)off;
@@ -1250,6 +1271,7 @@ struct GridJob {
         else slot_cell += work_cell;                   // one work set per slot
         if (budget <= 0) return fail(ctx, SPLASH_ERR_NOMEM, "not enough device memory for the per-cell work arrays");
         int64_t t_auto = std::min<int64_t>(kTileTarget, std::max<int64_t>(16384, round_up((nc + 3) / 4, 1024)));
+        t_auto = std::max<int64_t>(t_auto, round_up((nc + kPoolStreams - 1) / kPoolStreams, 1024));  // <= 16 tiles: one pool stream each
         if (slot_cell > 0) t_auto = std::min<int64_t>(t_auto, (int64_t)(budget / ((double)kSlots * slot_cell)));
         tile = opts.tile_cells > 0 ? opts.tile_cells : t_auto;
         tile = std::min<int64_t>(tile, nc);
@@ -1496,15 +1518,17 @@ struct GridJob {
             pp.q_list = nullptr;
             // forcing half of the cyclic year once, the spin-up chain on the state half, then the daily integration
             k_pool_table<FT><<<(unsigned)(ctx->sm_count * 2), 128, 0, Q>>>(pp, pool);
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1,
-                                                                                     ctx->pool_stage1 > 0 ? ctx->pool_stage1 : (1 << 30));
+            // stage budgets: a short first look, a long second one, then the cells that may run to the pass limit
+            const int b1 = ctx->pool_stage1 > 0 ? ctx->pool_stage1 : (1 << 30);
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1, b1, 32);
             CU(cudaEventRecord(e.ps1, Q));
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, 0);
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, ctx->pool_stage2, 32);
+            k_pool_spin<<<(unsigned)ctx->pool_last_ctas, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, ctx->pool_last_lanes);
             CU(cudaEventRecord(e.ps2, Q));
             launch_list<FT>(pp, monthly, ctx->sm_count * 2, Q);
             CU(cudaEventRecord(e.pm, Q));
             CU(cudaGetLastError());
-            launches += 4;
+            launches += 5;
         }
         {
             RunParams tp = rp;
@@ -1681,9 +1705,9 @@ struct GridJob {
                     return cudaEventElapsedTime(&m, ev_begin, x) == cudaSuccess ? (double)m : -1.0;
                 };
                 fprintf(stderr,
-                        "[splash trace] tile %2lld: start %7.1f first %7.1f..%7.1f rounds_end %7.1f bulk %7.1f..%7.1f | pool n=%llu hard=%llu "
+                        "[splash trace] tile %2lld: start %7.1f first %7.1f..%7.1f rounds_end %7.1f bulk %7.1f..%7.1f | pool n=%llu stage3=%llu "
                         "stage1_end %7.1f stage2_end %7.1f main_end %7.1f max_chain %llu\n",
-                        (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n,
+                        (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n[2],
                         opts.skip_spinup ? -1.0 : at(e.ps1), opts.skip_spinup ? -1.0 : at(e.ps2), opts.skip_spinup ? -1.0 : at(e.pm), c.max_chain);
             }
         }
