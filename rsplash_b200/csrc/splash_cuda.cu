@@ -63,6 +63,10 @@ constexpr int kMinBlocks = SPLASH_MIN_BLOCKS;  // resident CTAs per SM the regis
 #define SPLASH_UBLOCKS 1
 #endif
 constexpr int kListThreads = 32;  // list mode: one warp per CTA, so that the few long-running warps spread over all SMs
+#ifndef SPLASH_SYNC_EVERY
+#define SPLASH_SYNC_EVERY 1  // barrier every n-th day (power of two)
+#endif
+constexpr int kSyncMask = SPLASH_SYNC_EVERY - 1;
 constexpr int kSync = SPLASH_SYNC;
 constexpr int kUThreads = SPLASH_UTHREADS;
 constexpr int kUBlocks = SPLASH_UBLOCKS;
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
-        if (kSync >= 1) __syncthreads();
+        if (kSync >= 1 && (it & kSyncMask) == 0) __syncthreads();
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
         if (it < kSpinYear) {
             // first spin_up call: only its pass-0 pet is consumed (R/splash.point.R:148-150)
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_rest(RunParams p) {
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
-        if (kSync >= 1) __syncthreads();
+        if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
     }
     store_state(p.w, c, st);  // E_{k+1}: end of the pass
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
             }
             DayOut o;
             double rain, snowfall;
-            if (kS >= 1) __syncthreads();
+            if (kS >= 1 && (d & kSyncMask) == 0) __syncthreads();
             splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
 
             if (kBulk || phase == PH_MAIN) {
@@ -609,6 +613,8 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
 // launches finish them on their own streams.  Results are scattered to the caller's arrays at the
 // end of the call.
 // ---------------------------------------------------------------------------------------------
+constexpr int kDayPrePad = (kDayPreDoubles + 1) / 2 * 2;  // DayPre padded to whole 16-byte words
+
 struct Pool {
     void* f[3];          // [n_days][cap] forcing columns (same element type as the call's forcing)
     double* cc;          // [NCC][cap]
@@ -616,7 +622,8 @@ struct Pool {
     double* out[9];      // [n_out][cap]; null = layer not requested
     double* diag;        // [SPLASH_NDIAG][cap] (only the rows written by list mode are used)
     long long* cell;     // [cap] index of the cell in the caller's arrays
-    double* table;       // [365][kDayPreDoubles][cap] forcing half of the cyclic spin-up year (k_pool_table)
+    double* table;       // [cap][365][kDayPrePad] forcing half of the cyclic spin-up year (k_pool_table): one
+                         // contiguous 176-byte record per (cell, day), read by its lane with eleven 16-byte loads
     int* hard[2];        // [cap] each, per tile range, ping-pong: pool cells handed from one spin-up stage to the next
     unsigned long long* count;  // entries handed out so far
     long long cap;
@@ -691,11 +698,17 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
         DayPre pre;
         day_forcing(cc, p.dtab_spin[d], c_month_tab, f_sw, f_tc, f_pn, pre);
         const double* v = reinterpret_cast<const double*>(&pre);
-        double* dst = pool.table + ((long long)d * kDayPreDoubles) * pool.cap + j;
+        double* dst = pool.table + ((long long)j * kSpinYear + d) * kDayPrePad;
 #pragma unroll
-        for (int k = 0; k < kDayPreDoubles; ++k) dst[(long long)k * pool.cap] = v[k];
+        for (int k = 0; k < kDayPreDoubles; ++k) dst[k] = v[k];
     }
 }
+
+#ifdef SPLASH_CHAIN_SHARED_MATH
+using ChainMath = MathShared;
+#else
+using ChainMath = MathInline;
+#endif
 
 // The rest of the second spin_up call (SPLASH.cpp:1697-1743) for the pool's cells: a per-thread loop over
 // year passes with the reference's convergence test and exact cycle detection, the forcing half of every
@@ -734,25 +747,28 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
         double w1 = p.w.w1[c];
 #pragma unroll
         for (int k = 0; k < 5; ++k) snap(k) = p.w.snap[(int64_t)k * p.w.pitch + c];
-        const double* tab = pool.table + c;
-        const long long day_stride = (long long)kDayPreDoubles * pool.cap;
+        const double2* tab = reinterpret_cast<const double2*>(pool.table + (long long)c * kSpinYear * kDayPrePad);
         bool cont = true;
         int d = 0;
         while (cont) {
             DayPre pre;
             {
                 double* v = reinterpret_cast<double*>(&pre);
-                const double* src = tab + (long long)d * day_stride;
+                const double2* src = tab + d * (kDayPrePad / 2);
 #pragma unroll
-                for (int k = 0; k < kDayPreDoubles; ++k) v[k] = __ldg(src + (long long)k * pool.cap);
-                // next day's rows on their way while this day computes
-                const double* nxt = tab + (long long)((d + 1 == kSpinYear) ? 0 : d + 1) * day_stride;
-#pragma unroll
-                for (int k = 0; k < kDayPreDoubles; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (long long)k * pool.cap));
+                for (int k = 0; k < kDayPrePad / 2; ++k) {
+                    const double2 w = __ldg(src + k);
+                    v[2 * k] = w.x;
+                    if (2 * k + 1 < kDayPreDoubles) v[2 * k + 1] = w.y;
+                }
+                // next day's record on its way while this day computes
+                const double2* nxt = tab + ((d + 1 == kSpinYear) ? 0 : d + 1) * (kDayPrePad / 2);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + kDayPrePad / 2 - 1));
             }
             if (d == 0) saved = st;  // E_k: state of day 365 before the check day
             DayOut o;
-            day_state(cc, pre, st, o);
+            day_state<ChainMath>(cc, pre, st, o);
             ++spin_days;
             if (d == 0) {
                 bool hit_limit, cycle_found;
@@ -917,7 +933,7 @@ constexpr int kPoolStreams = 16;  // streams of the straggler-pool launches: a t
 #endif
 constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before the leftovers go to the pool
 constexpr int kPoolStage1Passes = 8;    // pass budget of the pool's first spin-up stage
-constexpr int kPoolStage2Passes = 64;   // ... and of the second; the third runs to the reference's pass limit
+constexpr int kPoolStage2Passes = 128;  // ... and of the second; the third runs to the reference's pass limit
 static_assert(kRounds <= kMaxRounds, "kRounds");
 constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
 
@@ -945,7 +961,7 @@ struct splash_ctx {
     int pool_stage1 = kPoolStage1Passes;  // SPLASH_POOL_STAGE1 (0 = single stage)
     int pool_stage2 = kPoolStage2Passes;  // SPLASH_POOL_STAGE2
     int pool_excl_smem = 0;               // dynamic shared memory of a last-stage CTA (SPLASH_POOL_EXCL=0: no exclusivity)
-    int pool_last_lanes = 8, pool_last_ctas = 192;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
+    int pool_last_lanes = 16, pool_last_ctas = 48;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
 };
@@ -1077,7 +1093,7 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
         // a quarter of the SM's shared memory per last-stage CTA: four of them fill an SM, and none fits
         // beside a uniform CTA (kSmemUniform)
         const char* v = getenv("SPLASH_POOL_EXCL");
-        const bool excl = v && atoi(v) != 0;  // off by default: measured no gain (the chain is latency-, not contention-bound)
+        const bool excl = !v || atoi(v) != 0;
         const int quarter = ((int)prop.sharedMemPerMultiprocessor - 4 * 1024) / 4 / 1024 * 1024;
         ctx->pool_excl_smem = excl ? std::max<int>((int)kSmemList, std::min<int>(quarter, (int)prop.sharedMemPerBlockOptin)) : (int)kSmemList;
     }
@@ -1213,7 +1229,7 @@ struct GridJob {
         // ---- straggler pool: a slice of the budget, ~4 % of the cells -----------------------------------
         const double per_entry = 3.0 * (double)std::max<int64_t>(nd, 1) * fsz + (double)(NCC + 11 + SPLASH_NDIAG + 1) * 8.0 + 12.0 +
                                  (double)n_out_layers * (double)std::max<int64_t>(n_out, 1) * 8.0 +
-                                 (double)kSpinYear * kDayPreDoubles * 8.0;
+                                 (double)kSpinYear * kDayPrePad * 8.0;
         int64_t cap = std::min<int64_t>(std::max<int64_t>(nc / 24, 2048), 131072);
         cap = std::min<int64_t>(cap, (int64_t)(0.10 * budget / per_entry));
         cap = std::min<int64_t>(std::max<int64_t>(cap, 32), round_up(nc, 32));
@@ -1233,7 +1249,7 @@ struct GridJob {
             const size_t o_out = carve((size_t)n_out_layers * std::max<int64_t>(n_out, 1) * cap * 8);
             const size_t o_dg = carve((size_t)SPLASH_NDIAG * cap * 8);
             const size_t o_cell = carve((size_t)cap * 8);
-            const size_t o_tab = carve((size_t)kSpinYear * kDayPreDoubles * cap * 8);
+            const size_t o_tab = carve((size_t)kSpinYear * kDayPrePad * cap * 8);
             const size_t o_hard = carve((size_t)cap * 4 * 2);
             const size_t o_cnt = carve(256);
             if (int rc = ensure(ctx, ctx->pool_mem, off)) return rc;

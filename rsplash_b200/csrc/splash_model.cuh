@@ -46,6 +46,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "splash_math.cuh"
 
 namespace splash {
@@ -155,6 +157,28 @@ __device__ __noinline__ double f_exp(double x) { return exp(x); }
 __device__ __noinline__ double f_log(double x) { return log(x); }
 __device__ __noinline__ double f_acos(double x) { return acos(x); }
 __device__ __noinline__ double f_sin(double x) { return sin(x); }
+#endif
+
+// How the state half of the day step reaches its transcendentals.  MathShared: calls of the shared
+// out-of-line copies (the throughput kernels, where 16 warps per SM share the instruction cache).
+// MathInline: the same algorithms expanded in place -- no call, no argument shuffling -- for the
+// straggler chain (k_pool_spin), where one warp per scheduler runs a dependent chain and every
+// instruction issued is latency.  Both evaluate identical operation sequences: results are bit-equal.
+struct MathShared {
+    static __device__ __forceinline__ double exp(double x) { return f_exp(x); }
+    static __device__ __forceinline__ double log(double x) { return f_log(x); }
+    static __device__ __forceinline__ double acos(double x) { return f_acos(x); }
+    static __device__ __forceinline__ double sin(double x) { return f_sin(x); }
+};
+#if SPLASH_LEVEL >= 1 && !defined(SPLASH_LIBDEVICE_MATH)
+struct MathInline {
+    static __device__ __forceinline__ double exp(double x) { return fm::exp_core(x); }
+    static __device__ __forceinline__ double log(double x) { return fm::log_core(x); }
+    static __device__ __forceinline__ double acos(double x) { return fm::acos_core(x); }
+    static __device__ __forceinline__ double sin(double x) { return fm::sin_core(x); }
+};
+#else
+using MathInline = MathShared;
 #endif
 
 // std::max / std::min semantics of the reference (NaN in the first argument wins, SURVEY B-1)
@@ -324,8 +348,8 @@ struct Transm {
     double t_uns, acs_out;
 };
 
-template <class CC>
-__device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, double ksat_visc) {
+template <class M, class CC>
+__device__ __forceinline__ Transm column_transmittance_core(const CC& cc, double sm, double ksat_visc) {
     const double bub = cc(C_BUB);
     const double e3 = cc(C_E3);
     const double depth = cc(C_DEPTH);
@@ -333,8 +357,8 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
 #if SPLASH_L1_POW
     const double theta_i = SPLASH_DIV_D1000(sm);
     const double x = SPLASH_DIV_DTH(theta_i - cc(C_THR));
-    const double a = cc(C_ILAM) * f_log(x);  // log shared by x^(1/lambda) and (x^(1/lambda))^(3 lambda + 1)
-    const double psi_m = SPLASH_FDIV(bub, f_exp(a));
+    const double a = cc(C_ILAM) * M::log(x);  // log shared by x^(1/lambda) and (x^(1/lambda))^(3 lambda + 1)
+    const double psi_m = SPLASH_FDIV(bub, M::exp(a));
     double wtd = SPLASH_DIV_1000(bub - psi_m);
     if (wtd < 0.0 || isnan(wtd)) {
         wtd = 0.01;
@@ -342,11 +366,11 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
         wtd = depth;
     }
     r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
-    const double r1 = f_exp(e3 * a);  // (bub/psi_m)^e3 with bub/psi_m == x^(1/lambda)
+    const double r1 = M::exp(e3 * a);  // (bub/psi_m)^e3 with bub/psi_m == x^(1/lambda)
     // second power: its base is 1 up to rounding noise unless wtd was clamped; first-order expansion there
     const double q = SPLASH_FDIV(bub, psi_m + (wtd * 1000.0));
     const double qm1 = q - 1.0;
-    const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : f_exp(e3 * f_log(q));
+    const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : M::exp(e3 * M::log(q));
     double t_uns = (ksat_visc * bub / e3) * (r1 - r2);
 #else
     const double theta_i = (sm) / cc(C_D1000);
@@ -366,6 +390,18 @@ __device__ __noinline__ Transm column_transmittance(const CC& cc, double sm, dou
     }
     r.t_uns = t_uns;
     return r;
+}
+
+template <class CC>
+__device__ __noinline__ Transm column_transmittance_shared(const CC& cc, double sm, double ksat_visc) {
+    return column_transmittance_core<MathShared>(cc, sm, ksat_visc);
+}
+template <class M, class CC>
+__device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, double ksat_visc) {
+    if constexpr (std::is_same<M, MathShared>::value)
+        return column_transmittance_shared(cc, sm, ksat_visc);
+    else
+        return column_transmittance_core<M>(cc, sm, ksat_visc);
 }
 
 // snowfall_prob's exponent, R/splash.point.R:576
@@ -525,7 +561,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.ksat_visc = cc(C_INTPERM) * SPLASH_FDIV(pw * kG, visc) * 3.6;  // SPLASH.cpp:1260
 }
 
-template <class CC>
+template <class M = MathShared, class CC>
 __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellState& st, DayOut& o) {
     const double wn = st.wn;
     const double tc = q.tc;
@@ -559,7 +595,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 
     // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:208-255 ------------------------------------------
     const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
-    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * f_exp(-0.895189 * nd));
+    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * M::exp(-0.895189 * nd));
     const double sfc = SPLASH_FDIV(snow, 140.0 + snow);
     const double alb_v = kalb_sw - 0.17 * sw;
     const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
@@ -576,10 +612,10 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     } else if (qn <= -1.0) {
         hn = 180.0;
     } else {
-        hn = f_acos(qn);
+        hn = M::acos(qn);
         hn = SPLASH_TO_DEG(hn);
     }
-    const double sin_hn = f_sin(hn * kpir);
+    const double sin_hn = M::sin(hn * kpir);
     double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
     rn_d *= (86400.0 / kPI);
     double rnn_d = rw * rv * (sin_hs - sin_hn);
@@ -605,7 +641,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     } else if (cos_hi <= -1.0) {
         hi = 180.0;
     } else {
-        hi = f_acos(cos_hi);
+        hi = M::acos(cos_hi);
         hi = SPLASH_TO_DEG(hi);
     }
     double snowmelt_tot;
@@ -619,7 +655,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
     melt_enrg += SPLASH_FDIV(SPLASH_DIVC(sublimation, 1000.0), econ);
     double aet_d = swp * hi * kpir;
-    aet_d += rx * rw * rv * (sin_hn - f_sin(hi * kpir));
+    aet_d += rx * rw * rv * (sin_hn - M::sin(hi * kpir));
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
     aet_d *= (24.0 / kPI);
     aet_d -= (melt_enrg * econ * 1000.0);
@@ -637,10 +673,10 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     {
         const double theta_r = cc(C_THR);
 #if SPLASH_L1_POW
-        // head/bp = (bp/u + 10)/bp = 1/u + 10/bp with u = x^(1/lambda); 1/u = f_exp(-f_log(x)/lambda)
-        const double lx = f_log(SPLASH_DIV_DTH(theta_mean - theta_r));
-        const double head = f_exp(-(cc(C_ILAM) * lx)) + cc(C_TEN_BP);
-        double theta_BC = cc(C_DTH) * f_exp(cc(C_NLAM) * f_log(head)) + theta_r;
+        // head/bp = (bp/u + 10)/bp = 1/u + 10/bp with u = x^(1/lambda); 1/u = M::exp(-M::log(x)/lambda)
+        const double lx = M::log(SPLASH_DIV_DTH(theta_mean - theta_r));
+        const double head = M::exp(-(cc(C_ILAM) * lx)) + cc(C_TEN_BP);
+        double theta_BC = cc(C_DTH) * M::exp(cc(C_NLAM) * M::log(head)) + theta_r;
 #else
         const double bp = cc(C_BP10);
         const double water_pot_BC = bp / pow((((theta_mean - theta_r) / cc(C_DTH))), cc(C_ILAM));
@@ -674,7 +710,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
                     tp = 0.01;
                 }
                 const double tp_s = tp / cc(C_COS2_S);
-                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * f_log(1 - SPLASH_FDIV(r * tp_s, h_f * delta_theta))));
+                I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * M::log(1 - SPLASH_FDIV(r * tp_s, h_f * delta_theta))));
             }
         }
         if (I > P) {
@@ -689,7 +725,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     // Kunsat only enters T_uns when depth >= 2 (:1433-1435); below field capacity its power is a cell constant
     double Kunsat = 0.0;
     if (deep) {
-        const double kp = (theta_i <= cc(C_THWMAX) || isnan(theta_i)) ? cc(C_KU_WMAX) : f_exp(cc(C_KUEXP) * f_log(theta_m / theta_s));
+        const double kp = (theta_i <= cc(C_THWMAX) || isnan(theta_i)) ? cc(C_KU_WMAX) : M::exp(cc(C_KUEXP) * M::log(theta_m / theta_s));
         Kunsat = Ksat_visc * kp;
     }
 #else
@@ -705,9 +741,9 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
     const double Q_qs = SPLASH_DIVC(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS), 1000.0);
 #if SPLASH_L1_RECIP
-    const double Kb = f_exp((Q_q0 - Q_qs) * cc(C_INV_DENKB));
+    const double Kb = M::exp((Q_q0 - Q_qs) * cc(C_INV_DENKB));
 #else
-    const double Kb = f_exp((Q_q0 - Q_qs) / cc(C_DENKB));
+    const double Kb = M::exp((Q_q0 - Q_qs) / cc(C_DENKB));
 #endif
     // ---- 5.2.2 drainage at Wmax, :1346-1360 --------------------------------------------------------
     const double To_uns = kbe3 * cc(C_BRW);
@@ -742,7 +778,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 #endif
     // ---- 5.6 transmittance after recharge, :1406-1457 ----------------------------------------------
     const double Ai = cc(C_AI);
-    Transm tr = column_transmittance(cc, sm, Ksat_visc);
+    Transm tr = column_transmittance<M>(cc, sm, Ksat_visc);
     double T;
     {
         double T_uns = tr.t_uns;
@@ -761,9 +797,9 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     double q_in_f = 0.0;
     const double td = st.td - 1.0;
     if ((R > 0.0) && (sm > cc(C_WMAX))) {
-        const double lkb = f_log(Kb);
+        const double lkb = M::log(Kb);
         const double Au = cc(C_AU);
-        t_drain = SPLASH_FDIV(-1.0 * f_log(1.0 - (lkb * SPLASH_FDIV(Au * R, Q))), lkb);
+        t_drain = SPLASH_FDIV(-1.0 * M::log(1.0 - (lkb * SPLASH_FDIV(Au * R, Q))), lkb);
         q_in_f = SPLASH_DIV_AI(Qt - Au * R * lkb);
     }
     if (q_in_f < 0.0 || isnan(q_in_f)) {
@@ -783,7 +819,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     // ---- 5.6' transmittance after upslope input, :1511-1547.  When sm did not move the block
     //      recomputes exactly the values of 5.6, so they are reused (bit-identical). -----------------
     if (!(sm == sm_before)) {
-        tr = column_transmittance(cc, sm, Ksat_visc);
+        tr = column_transmittance<M>(cc, sm, Ksat_visc);
     }
     {
         const double T_sat = Ksat_visc * 24.0 * SPLASH_DIV_AI(tr.acs_out);
