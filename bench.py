@@ -372,7 +372,7 @@ def main():
     #      timed with CUDA events on its streams inside the library (splash_stats.bulk_span_ms) --------------
     hbm_peak, hbm_src = peaks()
     dfma_peak, dfma_src = fp64_peak()
-    st_dev = torch.empty((5, nc), dtype=torch.float64, device=device)
+    st_dev = torch.empty((_abi.SPLASH_NSTATE, nc), dtype=torch.float64, device=device)
     cout_st = grid_out_struct(n_out, nc, [o.data_ptr() for o in outs], diag.data_ptr(), _abi.SPLASH_MEM_DEVICE)
     cout_st.state_final = st_dev.data_ptr()
     ctx.grid_run(cin, opts, cout_st)                      # spun-up state of every cell

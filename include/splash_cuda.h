@@ -41,7 +41,8 @@
 extern "C" {
 #endif
 
-#define SPLASH_ABI_VERSION 2
+#define SPLASH_ABI_VERSION 3
+#define SPLASH_NSTATE 6
 
 /* status codes */
 enum {
@@ -115,7 +116,9 @@ typedef struct splash_grid_out {
     double* bflow;          /* lateral drainage, mm */
     double* netr;           /* daytime net radiation, MJ m-2 */
     double* sm_lim;         /* relative soil moisture limitation 0..1 */
-    double* state_final;    /* optional [5*n_cells] layer-major: wn, snow, qin, td, nd after the last day (resume state, SPLASH.cpp:1833-1835) */
+    double* state_final;    /* optional [SPLASH_NSTATE*n_cells] layer-major: wn, snow, qin, td, nd after the last day (the carried
+                             * arguments of run_all, SPLASH.cpp:1833-1835) and the value of soil_info[12] (the aridity index
+                             * R/splash.point.R:150 writes there): everything a later call needs to continue the series */
     double* cell_diag;      /* optional [SPLASH_NDIAG*n_cells] layer-major */
     int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE for every pointer above */
     int32_t reserved;
@@ -128,7 +131,7 @@ typedef struct splash_opts {
     int64_t tile_cells;     /* cells per device tile; 0 = choose from free device memory */
     int32_t skip_spinup;    /* 1 = start run_all from state_init instead of spinning up (resume) */
     int32_t reserved;
-    const double* state_init; /* [5*n_cells] layer-major wn, snow, qin, td, nd (host); used when skip_spinup */
+    const double* state_init; /* [SPLASH_NSTATE*n_cells] layer-major, a previous call's state_final (host); used when skip_spinup */
 } splash_opts;
 
 /* Timing / accounting of the last call, filled by splash_last_stats (all times in milliseconds).

@@ -1152,6 +1152,8 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
         qin_last = st[2 * nc + c];
         td_last = st[3 * nc + c];
         nds_last = st[4 * nc + c];
+        soil_info[11] = st[5 * nc + c]; /* the aridity index the interrupted run had put there, splash.point.R:150 */
+        AI = soil_info[11];
     } else {
         int y1 = in->year[0];
         /* initial_AI <- spin_up(...), :148 */
@@ -1216,6 +1218,7 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
         st[2 * nc + c] = nd ? o[8][nd - 1] : qin_last;
         st[3 * nc + c] = nd ? o[9][nd - 1] : td_last;
         st[4 * nc + c] = nd ? o[10][nd - 1] : nds_last;
+        st[5 * nc + c] = soil_info[11];
     }
     if (out->cell_diag) {
         double* dg = out->cell_diag;

@@ -9,7 +9,8 @@ import ctypes as C
 
 import numpy as np
 
-SPLASH_ABI_VERSION = 2
+SPLASH_ABI_VERSION = 3
+SPLASH_NSTATE = 6
 
 SPLASH_OK, SPLASH_ERR_BAD_ARG, SPLASH_ERR_CUDA, SPLASH_ERR_NOMEM, SPLASH_ERR_NO_DEVICE = range(5)
 SPLASH_MEM_HOST, SPLASH_MEM_DEVICE = 0, 1

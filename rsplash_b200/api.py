@@ -103,7 +103,7 @@ def splash_grid(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, 
         result[k] = np.empty((n_out, n_cells), dtype=np.float64)
         setattr(cout, k, _ptr(result[k]))
     if return_state:
-        result["state_final"] = np.empty((5, n_cells))
+        result["state_final"] = np.empty((_abi.SPLASH_NSTATE, n_cells))
         cout.state_final = _ptr(result["state_final"])
     if return_diag:
         result["cell_diag"] = np.empty((_abi.SPLASH_NDIAG, n_cells))
@@ -115,7 +115,7 @@ def splash_grid(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, 
     opts.max_spin = int(max_spin)
     opts.spin_tol_mm = float(spin_tol_mm)
     if state_init is not None:
-        st = _f64(state_init, (5, n_cells), "state_init")
+        st = _f64(state_init, (_abi.SPLASH_NSTATE, n_cells), "state_init")
         opts.skip_spinup, opts.state_init = 1, _ptr(st)
     ctx.grid_run(cin, opts, cout)
     result["stats"] = ctx.stats()

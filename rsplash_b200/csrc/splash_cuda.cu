@@ -819,8 +819,10 @@ __global__ void k_pool_scatter(Pool pool, long long n, long long n_out, double* 
     }
     for (long long j = tid; j < n; j += nthreads) {
         const long long c = pool.cell[j];
-        if (state_final)
+        if (state_final) {
             for (int k = 0; k < 5; ++k) state_final[(long long)k * nc + c] = pool.w.st[(long long)k * pool.cap + j];
+            state_final[5LL * nc + c] = pool.cc[(long long)C_CELLOUT * pool.cap + j];
+        }
         if (cell_diag) {
             cell_diag[(long long)SPLASH_DIAG_SPIN_PASSES * nc + c] = pool.diag[(long long)SPLASH_DIAG_SPIN_PASSES * pool.cap + j];
             cell_diag[(long long)SPLASH_DIAG_SNOWFALL_DAYS * nc + c] = pool.diag[(long long)SPLASH_DIAG_SNOWFALL_DAYS * pool.cap + j];
@@ -845,12 +847,17 @@ __global__ void k_tile_begin(TileCtl* ctl, int n_cells) {  // (the control block
     ctl->cnt[0] = (unsigned long long)n_cells;
 }
 
-__global__ void k_init_resume(Work w, double* diag, int64_t dpitch, int n) {
+// resume: the carried aridity index (row 5 of state_init, parked in w.w1) goes where the interrupted run
+// had it, soil_info[12] == `cellout` (R/splash.point.R:150, SURVEY B-3)
+__global__ void k_init_resume(Work w, double* cc, int64_t cpitch, double* diag, int64_t dpitch, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     w.status[c] = ST_READY_BULK;
     w.passes[c] = 0;
-    if (diag) diag[SPLASH_DIAG_AI * dpitch + c] = nan("");
+    StridedCC ccg{cc + c, cpitch};
+    const double AI = w.w1[c];
+    lateral_consts(ccg, AI);
+    if (diag) diag[SPLASH_DIAG_AI * dpitch + c] = AI;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -964,6 +971,7 @@ struct splash_ctx {
     int pool_last_lanes = 16, pool_last_ctas = 48;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
+    int64_t pool_cap = 0;                 // SPLASH_POOL_CAP: force the pool capacity (tests of the overflow path)
 };
 
 namespace {
@@ -1098,6 +1106,7 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
         ctx->pool_excl_smem = excl ? std::max<int>((int)kSmemList, std::min<int>(quarter, (int)prop.sharedMemPerBlockOptin)) : (int)kSmemList;
     }
     if (const char* v = getenv("SPLASH_ROUNDS_RT")) ctx->n_rounds = std::max(0, std::min(kRounds, atoi(v)));
+    if (const char* v = getenv("SPLASH_POOL_CAP")) ctx->pool_cap = std::max<int64_t>(32, atoll(v));
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1233,6 +1242,7 @@ struct GridJob {
         int64_t cap = std::min<int64_t>(std::max<int64_t>(nc / 24, 2048), 131072);
         cap = std::min<int64_t>(cap, (int64_t)(0.10 * budget / per_entry));
         cap = std::min<int64_t>(std::max<int64_t>(cap, 32), round_up(nc, 32));
+        if (ctx->pool_cap > 0) cap = ctx->pool_cap;
         cap = round_up(cap, 32);
         if (opts.skip_spinup) cap = 32;  // nothing spins
         {
@@ -1481,7 +1491,8 @@ struct GridJob {
             // resume: run_all starts from the caller's state (SPLASH.cpp:1833-1835 wn_last ... nds_last)
             CU(cudaMemcpy2DAsync(rp.w.st, (size_t)pitch * 8, opts.state_init + c0, (size_t)nc * 8, (size_t)nct * 8, 5,
                                  cudaMemcpyHostToDevice, R));
-            k_init_resume<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp.w, rp.diag, rp.dpitch, (int)nct);
+            CU(cudaMemcpyAsync(rp.w.w1, opts.state_init + 5 * nc + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, R));
+            k_init_resume<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp.w, rp.cc, rp.cpitch, rp.diag, rp.dpitch, (int)nct);
             CU(cudaGetLastError());
             ++launches;
             CU(cudaEventRecord(e.kf1, R));
@@ -1586,7 +1597,8 @@ struct GridJob {
         }
         if (out->state_final) {
             CU(cudaMemcpy2DAsync(out->state_final + c0, (size_t)nc * 8, rp.w.st, (size_t)pitch * 8, (size_t)nct * 8, 5, okind, D));
-            if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * 5 * 8;
+            CU(cudaMemcpyAsync(out->state_final + 5 * nc + c0, rp.cc + (size_t)C_CELLOUT * pitch, (size_t)nct * 8, okind, D));
+            if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * SPLASH_NSTATE * 8;
         }
         if (out->cell_diag) {
             CU(cudaMemcpy2DAsync(out->cell_diag + c0, (size_t)nc * 8, rp.diag, (size_t)pitch * 8, (size_t)nct * 8, SPLASH_NDIAG, okind, D));
@@ -1643,6 +1655,8 @@ struct GridJob {
             CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.w.st, (size_t)pool.cap * 8, (size_t)n_pool * 8, 5, cudaMemcpyDeviceToHost));
             for (int k = 0; k < 5; ++k)
                 for (int64_t j = 0; j < n_pool; ++j) out->state_final[(int64_t)k * nc + cell[(size_t)j]] = buf[(size_t)(k * n_pool + j)];
+            CU(cudaMemcpy(buf.data(), pool.cc + (size_t)C_CELLOUT * pool.cap, (size_t)n_pool * 8, cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < n_pool; ++j) out->state_final[5 * nc + cell[(size_t)j]] = buf[(size_t)j];
         }
         if (out->cell_diag) {
             CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.diag, (size_t)pool.cap * 8, (size_t)n_pool * 8, SPLASH_NDIAG,

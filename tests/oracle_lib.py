@@ -139,7 +139,7 @@ class GridProblem:
 def alloc_out(n_out, n_cells, state=True, diag=True):
     arrays = {k: np.full((n_out, n_cells), np.nan) for k in _abi.OUTPUT_NAMES}
     if state:
-        arrays["state_final"] = np.full((5, n_cells), np.nan)
+        arrays["state_final"] = np.full((_abi.SPLASH_NSTATE, n_cells), np.nan)
     if diag:
         arrays["cell_diag"] = np.full((_abi.SPLASH_NDIAG, n_cells), np.nan)
     s = _abi.SplashGridOut()

@@ -24,7 +24,7 @@ def test_point_fixture_daily_matches_reference_golden(ctx, name):
     got = run_gpu(ctx, prob, dates, monthly=False)
     rep = parity.compare(got, gold, prefix="daily_")
     parity.compare_diag(got["cell_diag"], gold["cell_diag"])
-    st = np.abs(got["state_final"] - gold["daily_state_final"])
+    st = np.abs(got["state_final"][:5] - gold["daily_state_final"])
     assert np.nanmax(st[[0, 1]]) <= parity.ABS_STATE_MM
     print(name, rep)
 
