@@ -194,6 +194,33 @@ int splash_point_run(splash_ctx* ctx, int64_t n_days, const int32_t* year, const
 /* Accounting of the last splash_grid_run / splash_point_run on this context. */
 int splash_last_stats(const splash_ctx* ctx, splash_stats* out);
 
+/* ---- unSWC.grid: unsaturated-zone diagnostics of the simulated soil water (R/unsSWC.grid.R:14-141) ----
+ * Replaces the four raster::overlay() passes of unSWC.grid (calc_thetai :96-103, calcwtd :112-121, UnsWater
+ * :47-70 as called at :129, calc_Se :133-139) and its soil_hydro() call (:78); the netCDF writing stays in R.
+ * All arrays layer-major with cells contiguous (raster::getValues layout); any output pointer may be NULL. */
+typedef struct splash_unswc_in {
+    int64_t n_cells;
+    int64_t n_layers;       /* time steps (daily or monthly) of wn */
+    int64_t cell_stride;    /* elements between consecutive layers of wn; 0 means n_cells */
+    const double* soil;     /* [6*n_cells] layer-major as in splash_grid_in.soil (gravel is ignored: fgravel*0, :78) */
+    const double* wn;       /* [n_layers*cell_stride] soil water content of the whole profile, mm */
+    double uns_depth;       /* depth to integrate the water content to, m */
+    int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE (inputs and outputs alike) */
+    int32_t reserved;
+} splash_unswc_in;
+
+typedef struct splash_unswc_out {
+    int64_t cell_stride;    /* elements between consecutive layers of the outputs; 0 means n_cells */
+    double* theta_i;        /* mean volumetric moisture of the profile, m3/m3 (theta_mean file, :103) */
+    double* wtd;            /* water table depth, m (:121) */
+    double* w_z;            /* water content from the surface to uns_depth, mm (:129) */
+    double* se;             /* effective saturation of that layer, 0..1 (:139) */
+    int32_t mem_kind;
+    int32_t reserved;
+} splash_unswc_out;
+
+int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_unswc_out* out);
+
 /* Diagnostic (used by tests/test_math_gpu.py, not by the R glue): apply one of the day step's
  * transcendental functions to a host array on the device.  op: 0 exp, 1 log, 2 acos, 3 sin (hour
  * angles, [0, pi]).  These are the library's own implementations (csrc/splash_math.cuh), which stand

@@ -962,6 +962,77 @@ void splash_oracle_soil_hydro(double sand, double clay, double OM, double fgrave
     out[10] = bubbling_p;          /* bubbling_p */
 }
 
+/* R's ifelse(a >= b, x, y): an NA condition gives NA.  cond_ge / cond_le / cond_gt / cond_lt return
+ * 1, 0 or -1 (NA). */
+static int cond_ge(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a >= b); }
+static int cond_le(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a <= b); }
+static int cond_gt(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a > b); }
+static int cond_lt(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a < b); }
+
+/* calcwtd / the first lines of UnsWater, R/unsSWC.grid.R:49-50,113-115 */
+static double unswc_wtd(double psi_m, double totdepth, double bub_press) {
+    double wtdini = (bub_press - psi_m) / 1000;
+    int c1 = cond_gt(wtdini, totdepth);
+    if (c1 < 0) return NAN;
+    if (c1) return totdepth;
+    int c2 = cond_lt(wtdini, 0);
+    if (c2 < 0) return NAN;
+    return c2 ? 0 : wtdini;
+}
+
+void splash_oracle_unswc_grid(long long n_cells, long long n_layers, const double* soil, const double* wn, double uns_depth,
+                              double* theta_i_out, double* wtd_out, double* w_z_out, double* se_out) {
+    for (long long c = 0; c < n_cells; c++) {
+        double sh[11];
+        /* soil_hydro(..., fgravel = soil_data[[4]]*0, ...), :78 */
+        splash_oracle_soil_hydro(soil[0 * n_cells + c], soil[1 * n_cells + c], soil[2 * n_cells + c], soil[3 * n_cells + c] * 0,
+                                 soil[4 * n_cells + c], sh);
+        double theta_s = sh[0], theta_r = sh[9], lambda = 1 / sh[7], bub_press = sh[10];
+        double depth = soil[5 * n_cells + c];
+        for (long long l = 0; l < n_layers; l++) {
+            long long i = l * n_cells + c;
+            /* calc_thetai, :96-103 */
+            double theta_o = (wn[i] / (depth * 1000));
+            double theta_i;
+            int c1 = cond_ge(theta_o, theta_s);
+            if (c1 < 0) theta_i = NAN;
+            else if (c1) theta_i = theta_s - 0.0001;
+            else {
+                int c2 = cond_le(theta_o, theta_r);
+                theta_i = c2 < 0 ? NAN : (c2 ? theta_r + 0.0001 : theta_o);
+            }
+            /* :109 */
+            double psi_m = bub_press / (r_pow((((theta_i - theta_r) / (theta_s - theta_r))), (1 / lambda)));
+            /* :121 */
+            double wtd = unswc_wtd(psi_m, depth, bub_press);
+            /* :129 -- UnsWater(psi_m, z_uns, theta_r, theta_s, bub_press, lambda, depth = uns_depth), :47-70 */
+            double wtd2 = unswc_wtd(psi_m, uns_depth, bub_press);
+            int cz = cond_le(wtd2, uns_depth);
+            double z_uns = cz < 0 ? NAN : (cz ? wtd2 * 1000 : uns_depth * 1000);
+            double w_uns_z = theta_r * z_uns +
+                             (((psi_m + z_uns) * (theta_r - theta_s) * r_pow((bub_press / (psi_m + z_uns)), lambda)) / (lambda - 1));
+            double w_uns_0 = theta_r * 0 + (((psi_m + 0) * (theta_r - theta_s) * r_pow((bub_press / (psi_m + 0)), lambda)) / (lambda - 1));
+            double w_uns = w_uns_z - w_uns_0;
+            double sat_swc = cz < 0 ? NAN : (cz ? theta_s * (uns_depth - wtd2) * 1000 : 0);
+            double w_z = w_uns + sat_swc;
+            /* calc_Se, :133-138 */
+            double theta_i_top = w_z / (uns_depth * 1000);
+            double Se = theta_i_top / theta_s;
+            int s1 = cond_gt(Se, 1);
+            if (s1 < 0) Se = NAN;
+            else if (s1) Se = 1;
+            else {
+                int s2 = cond_lt(Se, 0);
+                Se = s2 < 0 ? NAN : (s2 ? 0 : Se);
+            }
+            theta_i_out[i] = theta_i;
+            wtd_out[i] = wtd;
+            w_z_out[i] = w_z;
+            se_out[i] = Se;
+        }
+    }
+}
+
 /* snowfall_prob, R/splash.point.R:560-578 */
 double splash_oracle_snowfall_prob(double tc, double lat, double elev) {
     return 1 / (1 + exp(-0.4710405934 + 1.0473543991 * tc - elev * 0.0004596581 - fabs(lat) * 0.0110592101));

@@ -63,6 +63,13 @@ void splash_oracle_solar_day(int n, int y, double out5[5]);
 /* soil_hydro (R/splash.point.R:232-416): out = {SAT, FC, WP, bd, AWC, Ksat, A, B, theta_c, RES, bubbling_p} */
 void splash_oracle_soil_hydro(double sand, double clay, double OM, double fgravel, double bd, double out11[11]);
 
+/* unSWC.grid (R/unsSWC.grid.R:14-141): the unsaturated-zone diagnostics of a block of cells.  soil is
+ * [6*n_cells] layer-major (sand, clay, OM, gravel %, bulk density, depth m), wn [n_layers*n_cells] the
+ * simulated soil water (mm); outputs [n_layers*n_cells]: theta_i (:96-103), wtd (:112-121), w_z (:47-70,:129)
+ * and Se (:133-139). */
+void splash_oracle_unswc_grid(long long n_cells, long long n_layers, const double* soil, const double* wn, double uns_depth,
+                              double* theta_i, double* wtd, double* w_z, double* se);
+
 /* snowfall_prob (R/splash.point.R:560-578) */
 double splash_oracle_snowfall_prob(double tc, double lat, double elev);
 

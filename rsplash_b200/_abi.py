@@ -89,6 +89,21 @@ class SplashOpts(C.Structure):
     ]
 
 
+class SplashUnswcIn(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int64), ("n_layers", C.c_int64), ("cell_stride", C.c_int64),
+        ("soil", C.c_void_p), ("wn", C.c_void_p), ("uns_depth", C.c_double),
+        ("mem_kind", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SplashUnswcOut(C.Structure):
+    _fields_ = [
+        ("cell_stride", C.c_int64), ("theta_i", C.c_void_p), ("wtd", C.c_void_p), ("w_z", C.c_void_p), ("se", C.c_void_p),
+        ("mem_kind", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class SplashStats(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_double),

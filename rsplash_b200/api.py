@@ -138,3 +138,26 @@ def splash_point(sw_in, tc, pn, lat, elev, slop=0.0, asp=0.0, soil_data=None, Au
                       np.asarray(soil_data, dtype=np.float64).reshape(6, 1), au.reshape(-1, 1), [resolution],
                       time_index, monthly_out=monthly_out, ctx=ctx, **kw)
     return {k: (v[:, 0] if isinstance(v, np.ndarray) and v.ndim == 2 else v) for k, v in res.items()}
+
+
+def unSWC_grid(soil_data, uns_depth: float, wn, ctx: Context | None = None) -> dict:
+    """unSWC.grid(soil_data, uns_depth, wn) of the reference (R/unsSWC.grid.R:14): unsaturated-zone diagnostics.
+
+    soil_data  [6, n_cells] as for splash_grid;  wn  [n_layers, n_cells] simulated soil water, mm;  uns_depth  m.
+    Returns {w_z, wtd, Se} like the R function, plus theta_i (which R writes to the theta_mean file).
+    """
+    ctx = ctx or default_context()
+    wn = np.ascontiguousarray(wn, dtype=np.float64)
+    if wn.ndim != 2:
+        raise ValueError("wn must be [n_layers, n_cells]")
+    n_layers, n_cells = wn.shape
+    soil = _f64(soil_data, (6, n_cells), "soil_data")
+    cin = _abi.SplashUnswcIn()
+    cin.n_cells, cin.n_layers, cin.cell_stride = n_cells, n_layers, n_cells
+    cin.soil, cin.wn, cin.uns_depth, cin.mem_kind = _ptr(soil), _ptr(wn), float(uns_depth), _abi.SPLASH_MEM_HOST
+    res = {k: np.empty((n_layers, n_cells)) for k in ("theta_i", "wtd", "w_z", "Se")}
+    cout = _abi.SplashUnswcOut()
+    cout.cell_stride, cout.mem_kind = n_cells, _abi.SPLASH_MEM_HOST
+    cout.theta_i, cout.wtd, cout.w_z, cout.se = _ptr(res["theta_i"]), _ptr(res["wtd"]), _ptr(res["w_z"]), _ptr(res["Se"])
+    ctx.check(ctx.lib.splash_unswc_grid_run(ctx.handle, C.byref(cin), C.byref(cout)))
+    return res

@@ -835,6 +835,92 @@ __global__ void k_finish_diag(const int* passes, double* diag, int64_t dpitch, i
     if (c < n) diag[SPLASH_DIAG_SPIN_PASSES * dpitch + c] = (double)passes[c];
 }
 
+// ---------------------------------------------------------------------------------------------
+// unSWC.grid (R/unsSWC.grid.R:14-141): unsaturated-zone diagnostics of the simulated soil water.
+// A per-cell-layer map: one thread per cell keeps the cell's Brooks-Corey parameters in registers
+// and walks the layers (day-major wn: each load / store is a coalesced row segment per warp).
+// R's ifelse() semantics are kept: a condition on an NA operand yields NA.
+// ---------------------------------------------------------------------------------------------
+struct UnswcParams {
+    const double* soil;  // [6][soil_pitch]
+    int64_t soil_pitch;
+    const double* wn;    // [n_layers][wpitch]
+    int64_t wpitch;
+    double *theta_i, *wtd, *w_z, *se;  // [n_layers][opitch] each; null = not wanted
+    int64_t opitch;
+    int64_t n_cells, n_layers;
+    double uns_depth;
+};
+
+__device__ __forceinline__ double unswc_wtd(double psi_m, double totdepth, double bub) {  // :49-50, :113-115
+    const double wtdini = (bub - psi_m) / 1000;
+    if (isnan(wtdini) || isnan(totdepth)) return nan("");
+    if (wtdini > totdepth) return totdepth;
+    return (wtdini < 0) ? 0.0 : wtdini;
+}
+
+__global__ void __launch_bounds__(256) k_unswc(UnswcParams p) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_cells) return;
+    // soil_hydro(sand, clay, OM, fgravel = soil_data[[4]] * 0, bd), :78
+    const SoilHydro sh = soil_hydro(p.soil[0 * p.soil_pitch + c], p.soil[1 * p.soil_pitch + c], p.soil[2 * p.soil_pitch + c],
+                                    p.soil[3 * p.soil_pitch + c] * 0, p.soil[4 * p.soil_pitch + c]);
+    const double theta_s = sh.sat, theta_r = sh.res_frac, lambda = 1 / sh.coef_B, bub = sh.bubbling_p;
+    const double depth = p.soil[5 * p.soil_pitch + c];
+    const double ilam = (1 / lambda);
+    const double ud = p.uns_depth;
+    for (int64_t l = 0; l < p.n_layers; ++l) {
+        const double w = __ldcs(p.wn + l * p.wpitch + c);
+        // calc_thetai, :96-103
+        const double theta_o = (w / (depth * 1000));
+        double theta_i;
+        if (isnan(theta_o) || isnan(theta_s)) {
+            theta_i = nan("");
+        } else if (theta_o >= theta_s) {
+            theta_i = theta_s - 0.0001;
+        } else if (isnan(theta_r)) {
+            theta_i = nan("");
+        } else {
+            theta_i = (theta_o <= theta_r) ? theta_r + 0.0001 : theta_o;
+        }
+#if SPLASH_LEVEL >= 1 && !defined(SPLASH_LIBDEVICE_MATH)
+        // x^y as exp(y*log(x)) with the library's own exp/log (level-1 arithmetic)
+        const double x = ((theta_i - theta_r) / (theta_s - theta_r));
+        const double psi_m = bub / fm::pow_core(x, ilam);  // :109
+#else
+        const double psi_m = bub / pow((((theta_i - theta_r) / (theta_s - theta_r))), ilam);  // :109
+#endif
+        const double wtd = unswc_wtd(psi_m, depth, bub);                                        // :121
+        // UnsWater(psi_m, z_uns, theta_r, theta_s, bub_press, lambda, depth = uns_depth), :47-70 as called at :129
+        const double wtd2 = unswc_wtd(psi_m, ud, bub);
+        const bool na2 = isnan(wtd2) || isnan(ud);
+        const bool shallow = !na2 && (wtd2 <= ud);
+        const double z_uns = na2 ? nan("") : (shallow ? wtd2 * 1000 : ud * 1000);
+#if SPLASH_LEVEL >= 1 && !defined(SPLASH_LIBDEVICE_MATH)
+        // both powers through the same function: at z_uns == 0 the two terms must cancel exactly, as in R
+        const double pz = fm::pow_core(bub / (psi_m + z_uns), lambda);
+        const double p0 = fm::pow_core(bub / (psi_m + 0), lambda);
+#else
+        const double pz = pow((bub / (psi_m + z_uns)), lambda);
+        const double p0 = pow((bub / (psi_m + 0)), lambda);
+#endif
+        const double w_uns_z = theta_r * z_uns + (((psi_m + z_uns) * (theta_r - theta_s) * pz) / (lambda - 1));
+        const double w_uns_0 = theta_r * 0 + (((psi_m + 0) * (theta_r - theta_s) * p0) / (lambda - 1));
+        const double w_uns = w_uns_z - w_uns_0;
+        const double sat_swc = na2 ? nan("") : (shallow ? theta_s * (ud - wtd2) * 1000 : 0.0);
+        const double w_z = w_uns + sat_swc;
+        // calc_Se, :133-138
+        const double theta_top = w_z / (ud * 1000);
+        double Se = theta_top / theta_s;
+        if (!isnan(Se)) Se = (Se > 1) ? 1.0 : ((Se < 0) ? 0.0 : Se);
+        const int64_t o = l * p.opitch + c;
+        if (p.theta_i) __stcs(p.theta_i + o, theta_i);
+        if (p.wtd) __stcs(p.wtd + o, wtd);
+        if (p.w_z) __stcs(p.w_z + o, w_z);
+        if (p.se) __stcs(p.se + o, Se);
+    }
+}
+
 // diagnostic: the day step's transcendental functions applied to an array (splash_debug_math)
 __global__ void k_debug_math(int op, int64_t n, const double* x, double* y) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1184,6 +1270,77 @@ int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, doubl
     CU(cudaFree(dy));
     return SPLASH_OK;
 }
+
+int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_unswc_out* out) {
+    if (!ctx) return SPLASH_ERR_BAD_ARG;
+    ctx->err.clear();
+    if (!in || !out) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_unswc_grid_run: NULL in/out");
+    const int64_t nc = in->n_cells, nl = in->n_layers;
+    if (nc < 0 || nl < 0) return fail(ctx, SPLASH_ERR_BAD_ARG, "negative n_cells/n_layers");
+    const int64_t istride = in->cell_stride ? in->cell_stride : nc, ostride = out->cell_stride ? out->cell_stride : nc;
+    if (istride < nc || ostride < nc) return fail(ctx, SPLASH_ERR_BAD_ARG, "cell_stride smaller than n_cells");
+    if ((in->mem_kind != SPLASH_MEM_HOST && in->mem_kind != SPLASH_MEM_DEVICE) || out->mem_kind != in->mem_kind)
+        return fail(ctx, SPLASH_ERR_BAD_ARG, "mem_kind must be SPLASH_MEM_HOST or SPLASH_MEM_DEVICE, the same for in and out");
+    if (nc == 0 || nl == 0) return SPLASH_OK;
+    if (!in->soil || !in->wn) return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL soil/wn");
+    CU(cudaSetDevice(ctx->device));
+    double* const optr[4] = {out->theta_i, out->wtd, out->w_z, out->se};
+    UnswcParams p{};
+    p.n_cells = nc;
+    p.uns_depth = in->uns_depth;
+    cudaStream_t S = ctx->s_run[0];
+    if (in->mem_kind == SPLASH_MEM_DEVICE) {
+        p.soil = in->soil;
+        p.soil_pitch = nc;
+        p.wn = in->wn;
+        p.wpitch = istride;
+        p.theta_i = optr[0];
+        p.wtd = optr[1];
+        p.w_z = optr[2];
+        p.se = optr[3];
+        p.opitch = ostride;
+        p.n_layers = nl;
+        k_unswc<<<(unsigned)((nc + 255) / 256), 256, 0, S>>>(p);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(S));
+        return SPLASH_OK;
+    }
+    // host arrays: chunks of layers through a device staging area (H2D, kernel, D2H per chunk)
+    int n_o = 0;
+    for (auto q : optr) n_o += q ? 1 : 0;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nl, ((int64_t)1 << 30) / std::max<int64_t>(1, nc * 8 * (1 + n_o))));
+    double *d_soil = nullptr, *d_wn = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_soil, (size_t)6 * nc * 8));
+    CU(cudaMalloc(&d_wn, (size_t)chunk * nc * 8));
+    if (n_o) CU(cudaMalloc(&d_out, (size_t)n_o * chunk * nc * 8));
+    CU(cudaMemcpyAsync(d_soil, in->soil, (size_t)6 * nc * 8, cudaMemcpyHostToDevice, S));
+    p.soil = d_soil;
+    p.soil_pitch = nc;
+    p.wn = d_wn;
+    p.wpitch = nc;
+    p.opitch = nc;
+    double** pp[4] = {&p.theta_i, &p.wtd, &p.w_z, &p.se};
+    int rc = SPLASH_OK;
+    for (int64_t l0 = 0; l0 < nl && rc == SPLASH_OK; l0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, nl - l0);
+        int k = 0;
+        for (int i = 0; i < 4; ++i) *pp[i] = optr[i] ? d_out + (size_t)(k++) * chunk * nc : nullptr;
+        p.n_layers = n;
+        if (cudaMemcpy2DAsync(d_wn, (size_t)nc * 8, in->wn + l0 * istride, (size_t)istride * 8, (size_t)nc * 8, (size_t)n,
+                              cudaMemcpyHostToDevice, S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
+        k_unswc<<<(unsigned)((nc + 255) / 256), 256, 0, S>>>(p);
+        for (int i = 0; i < 4 && rc == SPLASH_OK; ++i)
+            if (optr[i] && cudaMemcpy2DAsync(optr[i] + l0 * ostride, (size_t)ostride * 8, *pp[i], (size_t)nc * 8, (size_t)nc * 8, (size_t)n,
+                                             cudaMemcpyDeviceToHost, S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
+        if (cudaStreamSynchronize(S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
+    }
+    cudaFree(d_soil);
+    cudaFree(d_wn);
+    if (d_out) cudaFree(d_out);
+    if (rc != SPLASH_OK) return fail(ctx, rc, "splash_unswc_grid_run: %s", cudaGetErrorString(cudaGetLastError()));
+    return SPLASH_OK;
+}
+
 
 }  // extern "C"
 

@@ -886,15 +886,20 @@ struct CellDiag {
     double sat, wp, fc, ksat, lambda, depth, bub, res, wmax_r;
 };
 
-template <class CC>
-__device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDiag& dg) {
-    // ---- soil_hydro, R/splash.point.R:261-380, 410 -------------------------------------------------
-    const double fsand = in.sand / 100;
-    const double fclay = in.clay / 100;
-    const double fOM = in.om / 100;
-    const double fgravel = in.gravel / 100;
+// soil_hydro(sand, clay, OM, fgravel, bd), R/splash.point.R:232-416: the pedotransfer functions.  Shared by
+// the per-cell setup of the hot path and by the unSWC diagnostics (which call it with fgravel = 0).
+struct SoilHydro {
+    double sat, fc, wp, res_frac, ksat, coef_A, coef_B, theta_c, bubbling_p;
+};
+
+__device__ __forceinline__ SoilHydro soil_hydro(double sand, double clay, double om, double gravel, double bd_in) {
+    // ---- R/splash.point.R:261-380, 410 -------------------------------------------------------------
+    const double fsand = sand / 100;
+    const double fclay = clay / 100;
+    const double fOM = om / 100;
+    const double fgravel = gravel / 100;
     const double dp = 1 / ((fOM / 1.3) + ((1 - fOM) / 2.65));
-    double bd = in.bd;
+    double bd = bd_in;
     if (isnan(bd)) {
         bd = (1.5 + (dp - 1.5 - 1.10 * (1 - fclay)) * (1 - exp(-0.022 * 30.0))) / (1 + 6.27 * fOM);
     }
@@ -904,14 +909,14 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     double fc = (sat / bd) * (0.4760944 + (0.9402962 - 0.4760944) * sq_clay) *
                 exp(-1 * (0.05472678 * fsand - 0.01 * fOM) / (sat / bd));
     const double wp_Ball = fc * (0.2018522 + (0.7809203 - 0.2018522) * sq_clay);
-    double wp = -2.464e-05 * in.sand + 3.650e-03 * in.clay + 8.680e-03 * in.om + 9.393e-03 * bd;
+    double wp = -2.464e-05 * sand + 3.650e-03 * clay + 8.680e-03 * om + 9.393e-03 * bd;
     if (!isnan(wp) && wp >= fc) wp = wp_Ball;
     const double coef_B = (log(1500.0) - log(33.0)) / (log(fc) - log(wp));
     const double coef_A = exp(log(33.0) + coef_B * log(fc));
     const double coef_lambda = 1 / coef_B;
     const double coeff_c = 1000.0 / (997 * 9.80665);
     const double theta_c = pow((coeff_c * coef_A / 2.0), (1 / (1 + coef_B)));
-    double theta_r0 = (0.0285 + 0.00336 * (in.clay)) * bd;
+    double theta_r0 = (0.0285 + 0.00336 * (clay)) * bd;
     if (!isnan(theta_r0) && theta_r0 > wp) theta_r0 = wp;
     sat = sat * (1 - fgravel);
     fc = fc * (1 - fgravel);
@@ -927,6 +932,25 @@ __device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDia
     bubbling_p = bubbling_p * -101.97162129779;
     if (!isnan(bubbling_p) && bubbling_p > 0) bubbling_p = coef_A * -101.97162129779;
     const double res_frac = theta_r0 * (1 - fgravel);
+
+    SoilHydro h;
+    h.sat = sat;
+    h.fc = fc;
+    h.wp = wp;
+    h.res_frac = res_frac;
+    h.ksat = ksat;
+    h.coef_A = coef_A;
+    h.coef_B = coef_B;
+    h.theta_c = theta_c;
+    h.bubbling_p = bubbling_p;
+    return h;
+}
+
+template <class CC>
+__device__ __forceinline__ void cell_setup(CC& cc, const CellInputs& in, CellDiag& dg) {
+    const SoilHydro sh = soil_hydro(in.sand, in.clay, in.om, in.gravel, in.bd);
+    const double sat = sh.sat, fc = sh.fc, wp = sh.wp, res_frac = sh.res_frac, ksat = sh.ksat, coef_B = sh.coef_B,
+                 theta_c = sh.theta_c, bubbling_p = sh.bubbling_p;
 
     // ---- soil_info, R/splash.point.R:97-115 --------------------------------------------------------
     const double depth = in.depth;

@@ -67,6 +67,8 @@ def oracle():
         lib.splash_oracle_grid_run_core.argtypes = [C.POINTER(_abi.SplashGridIn), C.POINTER(_abi.SplashOpts),
                                                     C.POINTER(_abi.SplashGridOut), C.c_int, C.c_void_p, C.c_void_p]
         lib.splash_oracle_grid_run_core.restype = C.c_int
+        lib.splash_oracle_unswc_grid.argtypes = [C.c_longlong, C.c_longlong, dp, dp, C.c_double, dp, dp, dp, dp]
+        lib.splash_oracle_unswc_grid.restype = None
         lib.splash_oracle_last_spin_cell_days.argtypes = []
         lib.splash_oracle_last_spin_cell_days.restype = C.c_int64
         _oracle = lib
@@ -172,3 +174,16 @@ def run_cpu(problem: GridProblem, monthly=False, core="oracle", n_threads=0, sta
         raise RuntimeError(f"oracle grid run failed rc={rc}")
     arrays["spin_cell_days"] = int(lib.splash_oracle_last_spin_cell_days())
     return arrays
+
+
+def unswc_cpu(soil, uns_depth, wn) -> dict:
+    """unSWC.grid on the C restatement (R/unsSWC.grid.R): {theta_i, wtd, w_z, Se}, each [n_layers, n_cells]."""
+    lib = oracle()
+    soil = np.ascontiguousarray(soil, dtype=np.float64)
+    wn = np.ascontiguousarray(wn, dtype=np.float64)
+    n_layers, n_cells = wn.shape
+    out = {k: np.full((n_layers, n_cells), np.nan) for k in ("theta_i", "wtd", "w_z", "Se")}
+    p = lambda a: a.ctypes.data_as(dp)
+    lib.splash_oracle_unswc_grid(n_cells, n_layers, p(soil), p(wn), float(uns_depth), p(out["theta_i"]), p(out["wtd"]),
+                                 p(out["w_z"]), p(out["Se"]))
+    return out
