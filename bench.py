@@ -418,6 +418,9 @@ def main():
     # ---- e2e: the same job through the C ABI with pinned HOST buffers, block of rows by block ----------
     e2e = None
     if not args.no_e2e:
+        # the value leg's output layers are not needed any more (the forcing stays: the host blocks are staged from it)
+        del cout, cout_st, outs, diag
+        torch.cuda.empty_cache()
         # pinned f64 forcing per block: <= ~72 GB, and the ranks of a box share its host memory
         pin_budget = 72e9
         try:

@@ -227,8 +227,12 @@ struct Work {
 };
 
 struct RunParams {
-    const void *sw, *tc, *pn;  // [n_days][fpitch]
+    const void *sw, *pn;       // [n_days][fpitch]
     int64_t fpitch;
+    const void* tc;            // [n_days][tpitch]
+    int64_t tpitch;
+    const void *sw1, *pn1;     // the first min(n_days, 365) rows of sw / pn, [..][f1pitch]: all the spin-up reads of them
+    int64_t f1pitch;           // (host-fed calls upload them ahead of the full series; otherwise sw1 == sw, pn1 == pn)
     double* cc;                // [NCC][cpitch]
     int64_t cpitch;
     const DayTab* dtab;        // [n_days]
@@ -294,10 +298,10 @@ __device__ __forceinline__ bool same_bits(double a, double b) {
 template <typename FT>
 __device__ __forceinline__ void spin_forcing(const RunParams& p, int c, int d, double& f_sw, double& f_tc, double& f_pn) {
     if (d < p.n_days) {
-        const int64_t off = (int64_t)d * p.fpitch + c;
-        f_sw = ld_stream((const FT*)p.sw + off);
-        f_tc = ld_stream((const FT*)p.tc + off);
-        f_pn = ld_stream((const FT*)p.pn + off);
+        const int64_t off = (int64_t)d * p.f1pitch + c;
+        f_sw = ld_stream((const FT*)p.sw1 + off);
+        f_tc = ld_stream((const FT*)p.tc + (int64_t)d * p.tpitch + c);
+        f_pn = ld_stream((const FT*)p.pn1 + off);
     } else {
         f_sw = f_tc = f_pn = nan("");
     }
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
                 dt = p.dtab[d];
                 const int64_t off = (int64_t)d * p.fpitch;
                 f_sw = ld_stream(sw_col + off);
-                f_tc = ld_stream(tc_col + off);
+                f_tc = ld_stream(tc_col + (int64_t)d * p.tpitch);
                 f_pn = ld_stream(pn_col + off);
             } else {
                 dt = p.dtab_spin[d];
@@ -643,8 +647,11 @@ __global__ void k_pool_reserve(TileCtl* ctl, int last_list, unsigned long long* 
     ctl->tail_end = n;
 }
 
+// part 1: per-entry records and the spin-up year's forcing rows (from sw1 / tc / pn1); part 2: the forcing rows
+// of the whole series (from sw / tc / pn).  Host-fed calls run part 1 as soon as a tile has spun up and part 2
+// once the tile's full series has arrived; otherwise both run together (part 3).
 template <typename FT>
-__global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int last_list, long long cell0) {
+__global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int last_list, long long cell0, int part) {
     const TileCtl* ctl = p.ctl;
     const unsigned long long base = ctl->pool_base;
     const long long n = (long long)(ctl->pool_end - base);
@@ -653,7 +660,7 @@ __global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // per-entry records
-    for (long long e = tid; e < n; e += nthreads) {
+    for (long long e = tid; (part & 1) && e < n; e += nthreads) {
         const int c = list ? list[e] : (int)e;
         const long long j = (long long)base + e;
         for (int k = 0; k < NCC; ++k) pool.cc[(long long)k * pool.cap + j] = p.cc[(int64_t)k * p.cpitch + c];
@@ -669,14 +676,18 @@ __global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int
         p.w.status[c] = ST_EXPORTED;
     }
     // forcing columns: consecutive threads write consecutive pool entries of one day
-    const long long total = n * (long long)p.n_days;
-    for (long long q = tid; q < total; q += nthreads) {
+    const bool whole = (part & 2) != 0;
+    const long long rows = whole ? (long long)p.n_days : (long long)(p.n_days < kSpinYear ? p.n_days : kSpinYear);
+    const void* src_sw = whole ? p.sw : p.sw1;
+    const void* src_pn = whole ? p.pn : p.pn1;
+    const long long spitch = whole ? p.fpitch : p.f1pitch;
+    for (long long q = tid; q < n * rows; q += nthreads) {
         const long long d = q / n, e = q - d * n;
         const int c = list ? list[e] : (int)e;
-        const long long src = d * p.fpitch + c, dst = d * pool.cap + (long long)base + e;
-        ((FT*)pool.f[0])[dst] = ((const FT*)p.sw)[src];
-        ((FT*)pool.f[1])[dst] = ((const FT*)p.tc)[src];
-        ((FT*)pool.f[2])[dst] = ((const FT*)p.pn)[src];
+        const long long dst = d * pool.cap + (long long)base + e;
+        ((FT*)pool.f[0])[dst] = ((const FT*)src_sw)[d * spitch + c];
+        ((FT*)pool.f[1])[dst] = ((const FT*)p.tc)[d * p.tpitch + c];
+        ((FT*)pool.f[2])[dst] = ((const FT*)src_pn)[d * spitch + c];
     }
 }
 
@@ -1048,7 +1059,7 @@ struct splash_ctx {
     // grow-only device buffers
     DevBuf forcing[kSlots][3], cellin[kSlots], outs[kSlots];
     std::vector<WorkSet> work;
-    DevBuf dtab, dtab_spin, ctl, pool_mem;
+    DevBuf dtab, dtab_spin, ctl, pool_mem, ahead_mem;
     // tuning knobs (environment overrides for experiments, read once at creation)
     int n_run_streams = kRunStreams;      // SPLASH_RUN_STREAMS
     int pool_stage1 = kPoolStage1Passes;  // SPLASH_POOL_STAGE1 (0 = single stage)
@@ -1058,6 +1069,7 @@ struct splash_ctx {
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
     int64_t pool_cap = 0;                 // SPLASH_POOL_CAP: force the pool capacity (tests of the overflow path)
+    int spin_ahead = 1;                   // SPLASH_SPIN_AHEAD=0: host-fed calls upload tile by tile (no spin-up data first)
 };
 
 namespace {
@@ -1193,6 +1205,7 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     }
     if (const char* v = getenv("SPLASH_ROUNDS_RT")) ctx->n_rounds = std::max(0, std::min(kRounds, atoi(v)));
     if (const char* v = getenv("SPLASH_POOL_CAP")) ctx->pool_cap = std::max<int64_t>(32, atoll(v));
+    if (const char* v = getenv("SPLASH_SPIN_AHEAD")) ctx->spin_ahead = atoi(v) != 0;
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1230,6 +1243,7 @@ void splash_ctx_destroy(splash_ctx* ctx) {
     fr(ctx->dtab_spin);
     fr(ctx->ctl);
     fr(ctx->pool_mem);
+    fr(ctx->ahead_mem);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     for (auto s : ctx->s_run)
@@ -1361,30 +1375,37 @@ struct GridJob {
     int n_out_layers = 0;
     int64_t tile = 0, n_tiles = 0, pitch = 0;
     int n_work = 0;
+    // host-fed calls: the data every tile's spin-up needs (the whole tc series for the snow threshold, the
+    // first year of sw and pn, the per-cell inputs) is uploaded for ALL tiles before the bulk of the forcing,
+    // so that every tile's stragglers start their chain early instead of when their tile's turn comes
+    bool ahead = false;
+    int64_t ncp = 0, nd1 = 0;        // pitch of the call-wide buffers, rows of the first-year copies
+    void *a_tc = nullptr, *a_sw1 = nullptr, *a_pn1 = nullptr;
+    double* a_cellin = nullptr;
     Pool pool{};
     int64_t launches = 0;
 
     struct TileEv {
-        cudaEvent_t h2d0, h2d1;                   // h2d stream: the tile's uploads
+        cudaEvent_t h2d0, h2d1, h2da, h2db;       // h2d stream: the tile's uploads (`ahead` mode: h2d0..h2da spin-up data, h2db..h2d1 the rest)
         cudaEvent_t k0, kf0, kf1, kr1, kb0, kb1;  // run stream: begin, k_spin_first begin/end, rounds end, bulk begin/end
-        cudaEvent_t exported, run, d2h0, d2h1;    // stragglers exported; all tile kernels done; downloads
+        cudaEvent_t exported, exported_b, run, d2h0, d2h1;  // stragglers exported (state / whole forcing); kernels done; downloads
         cudaEvent_t ps1, ps2, pm;                 // pool stream: spin stage 1 done, stage 2 done, daily integration done
     };
     std::vector<TileEv> ev;
-    std::vector<RunParams> rps;
+    std::vector<RunParams> rps, pps;  // per tile: the tile's view, the pool's view
     std::vector<SetupParams> sps;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
     TileCtl* ctl(int64_t t) const { return (TileCtl*)ctx->ctl.p + t; }
     cudaStream_t run_stream(int64_t t) const { return ctx->s_run[t % ctx->n_run_streams]; }
-    int work_of(int64_t t) const { return in_dev ? (int)t : (int)(t % kSlots); }
+    int work_of(int64_t t) const { return (in_dev || ahead) ? (int)t : (int)(t % kSlots); }
     int64_t cells_of(int64_t t) const { return std::min<int64_t>(tile, nc - t * tile); }
 
     int plan() {
         const size_t fsz = sizeof(FT);
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        size_t held = ctx->pool_mem.cap + ctx->ctl.cap;
+        size_t held = ctx->pool_mem.cap + ctx->ctl.cap + ctx->ahead_mem.cap;
         for (int i = 0; i < kSlots; ++i) {
             for (int k = 0; k < 3; ++k) held += ctx->forcing[i][k].cap;
             held += ctx->cellin[i].cap + ctx->outs[i].cap;
@@ -1445,13 +1466,26 @@ struct GridJob {
             budget -= (double)off;
         }
 
-        // ---- tile size ------------------------------------------------------------------------------------
+        // ---- host-fed calls: spin-up data of all tiles ahead of the bulk of the forcing, if it fits --------
         const double work_cell = (double)(NCC + 11 + SPLASH_NDIAG) * 8.0 + 5 * 4.0;
+        nd1 = std::min<int64_t>(nd, kSpinYear);
+        ncp = round_up(nc, 32);
+        const double ahead_bytes = (double)ncp * ((double)(nd + 2 * nd1) * fsz + 14 * 8.0);
+        {
+            // worth it only if what is left still gives decent tiles (three slots of sw + pn [+ outputs])
+            const double left = budget - ahead_bytes - work_cell * (double)nc;
+            const double slot1 = 2.0 * (double)nd * (double)fsz + (out_dev ? 0.0 : (double)n_out_layers * (double)n_out * 8.0);
+            const double tile_left = left / ((double)kSlots * std::max(slot1, 1.0));
+            ahead = !in_dev && !opts.skip_spinup && ctx->spin_ahead && nd > 0 && left > 0 &&
+                    tile_left >= (double)std::min<int64_t>(nc, std::max<int64_t>(32768, nc / 16));
+        }
+        if (ahead) budget -= ahead_bytes;
+        // ---- tile size ------------------------------------------------------------------------------------
         double slot_cell = 0.0;  // bytes per cell held once per slot
-        if (!in_dev) slot_cell += 3.0 * (double)nd * (double)fsz + 14 * 8.0;
+        if (!in_dev) slot_cell += (ahead ? 2.0 * (double)nd * (double)fsz : 3.0 * (double)nd * (double)fsz + 14 * 8.0);
         if (!out_dev) slot_cell += (double)n_out_layers * (double)n_out * 8.0;
-        if (in_dev) budget -= work_cell * (double)nc;  // one work set per tile
-        else slot_cell += work_cell;                   // one work set per slot
+        if (in_dev || ahead) budget -= work_cell * (double)nc;  // one work set per tile
+        else slot_cell += work_cell;                            // one work set per slot
         if (budget <= 0) return fail(ctx, SPLASH_ERR_NOMEM, "not enough device memory for the per-cell work arrays");
         int64_t t_auto = std::min<int64_t>(kTileTarget, std::max<int64_t>(16384, round_up((nc + 3) / 4, 1024)));
         t_auto = std::max<int64_t>(t_auto, round_up((nc + kPoolStreams - 1) / kPoolStreams, 1024));  // <= 16 tiles: one pool stream each
@@ -1467,7 +1501,7 @@ struct GridJob {
         if (tile > (int64_t)INT32_MAX / 2) tile = (int64_t)INT32_MAX / 2 / 1024 * 1024;
         n_tiles = (nc + tile - 1) / tile;
         pitch = round_up(tile, 32);
-        n_work = in_dev ? (int)n_tiles : (int)std::min<int64_t>(kSlots, n_tiles);
+        n_work = (in_dev || ahead) ? (int)n_tiles : (int)std::min<int64_t>(kSlots, n_tiles);
         return SPLASH_OK;
     }
 
@@ -1485,11 +1519,22 @@ struct GridJob {
         for (int s = 0; s < n_slots; ++s) {
             if (!in_dev) {
                 for (int k = 0; k < 3; ++k)
-                    if (int rc = ensure(ctx, ctx->forcing[s][k], (size_t)std::max<int64_t>(nd, 1) * pitch * fsz)) return rc;
-                if (int rc = ensure(ctx, ctx->cellin[s], (size_t)14 * pitch * 8)) return rc;
+                    if (!(ahead && k == 1))  // (the tc series lives in the call-wide buffer)
+                        if (int rc = ensure(ctx, ctx->forcing[s][k], (size_t)std::max<int64_t>(nd, 1) * pitch * fsz)) return rc;
+                if (!ahead)
+                    if (int rc = ensure(ctx, ctx->cellin[s], (size_t)14 * pitch * 8)) return rc;
             }
             if (!out_dev && n_out_layers)
                 if (int rc = ensure(ctx, ctx->outs[s], (size_t)n_out_layers * std::max<int64_t>(n_out, 1) * pitch * 8)) return rc;
+        }
+        if (ahead) {
+            const size_t b_tc = (size_t)nd * ncp * fsz, b_1 = (size_t)nd1 * ncp * fsz;
+            if (int rc = ensure(ctx, ctx->ahead_mem, b_tc + 2 * b_1 + (size_t)14 * ncp * 8 + 1024)) return rc;
+            char* b = (char*)ctx->ahead_mem.p;
+            a_tc = b;
+            a_sw1 = b + b_tc;
+            a_pn1 = b + b_tc + b_1;
+            a_cellin = (double*)(b + (b_tc + 2 * b_1 + 255) / 256 * 256);
         }
         if (int rc = ensure(ctx, ctx->ctl, sizeof(TileCtl) * (size_t)n_tiles)) return rc;
         CU(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(TileCtl) * (size_t)n_tiles, ctx->s_h2d));
@@ -1499,19 +1544,23 @@ struct GridJob {
         for (auto& t : ev) {
             cudaEvent_t* timed[13] = {&t.h2d0, &t.h2d1, &t.k0, &t.kf0, &t.kf1, &t.kr1, &t.kb0, &t.kb1, &t.d2h0, &t.d2h1, &t.ps1, &t.ps2, &t.pm};
             for (auto* e : timed) CU(cudaEventCreate(e));
+            CU(cudaEventCreate(&t.h2da));
+            CU(cudaEventCreate(&t.h2db));
+            CU(cudaEventCreateWithFlags(&t.exported_b, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&t.exported, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&t.run, cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&ev_begin));
         CU(cudaEventCreate(&ev_end));
         rps.resize((size_t)n_tiles);
+        pps.resize((size_t)n_tiles);
         sps.resize((size_t)n_tiles);
         return SPLASH_OK;
     }
 
     void release() {
         for (auto& t : ev) {
-            cudaEvent_t all[15] = {t.h2d0, t.h2d1, t.k0, t.kf0, t.kf1, t.kr1, t.kb0, t.kb1, t.d2h0, t.d2h1, t.exported, t.run, t.ps1, t.ps2, t.pm};
+            cudaEvent_t all[18] = {t.h2d0, t.h2d1, t.k0, t.kf0, t.kf1, t.kr1, t.kb0, t.kb1, t.d2h0, t.d2h1, t.exported, t.run, t.ps1, t.ps2, t.pm, t.h2da, t.exported_b, t.h2db};
             for (auto e : all)
                 if (e) cudaEventDestroy(e);
         }
@@ -1521,8 +1570,68 @@ struct GridJob {
         ev_begin = ev_end = nullptr;
     }
 
-    // uploads of tile t into its slot; fills the tile's kernel parameters
+    // `ahead` mode, phase A: what the tile's spin-up needs, into the call-wide buffers
+    int enqueue_h2d_ahead(int64_t t) {
+        const size_t fsz = sizeof(FT);
+        const int64_t c0 = t * tile, nct = cells_of(t);
+        cudaStream_t H = ctx->s_h2d;
+        CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
+        CU(cudaMemcpy2DAsync((char*)a_tc + (size_t)c0 * fsz, (size_t)ncp * fsz, (const char*)in->tc + (size_t)c0 * fsz, (size_t)istride * fsz,
+                             (size_t)nct * fsz, (size_t)nd, cudaMemcpyHostToDevice, H));
+        CU(cudaMemcpy2DAsync((char*)a_sw1 + (size_t)c0 * fsz, (size_t)ncp * fsz, (const char*)in->sw_in + (size_t)c0 * fsz,
+                             (size_t)istride * fsz, (size_t)nct * fsz, (size_t)nd1, cudaMemcpyHostToDevice, H));
+        CU(cudaMemcpy2DAsync((char*)a_pn1 + (size_t)c0 * fsz, (size_t)ncp * fsz, (const char*)in->pn + (size_t)c0 * fsz, (size_t)istride * fsz,
+                             (size_t)nct * fsz, (size_t)nd1, cudaMemcpyHostToDevice, H));
+        ctx->stats.h2d_bytes += (int64_t)nct * (nd + 2 * nd1) * (int64_t)fsz;
+        double* ci = a_cellin + c0;
+        const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
+        for (int k = 0; k < 5; ++k)
+            CU(cudaMemcpyAsync(ci + (size_t)k * ncp, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
+        CU(cudaMemcpy2DAsync(ci + (size_t)5 * ncp, (size_t)ncp * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6, cudaMemcpyHostToDevice, H));
+        CU(cudaMemcpy2DAsync(ci + (size_t)11 * ncp, (size_t)ncp * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8, (size_t)in->au_layers,
+                             cudaMemcpyHostToDevice, H));
+        ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
+        CU(cudaEventRecord(ev[(size_t)t].h2da, H));
+        return SPLASH_OK;
+    }
+
+    // uploads of tile t into its slot (in `ahead` mode: the whole sw and pn series; tc is already there)
     int enqueue_h2d(int64_t t) {
+        const size_t fsz = sizeof(FT);
+        const int s = (int)(t % kSlots);
+        const int64_t c0 = t * tile, nct = cells_of(t);
+        cudaStream_t H = ctx->s_h2d;
+        if (in_dev) {
+            CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
+        } else {
+            if (t >= kSlots) CU(cudaStreamWaitEvent(H, ev[(size_t)(t - kSlots)].run, 0));  // the slot's previous kernels are done
+            CU(cudaEventRecord(ahead ? ev[(size_t)t].h2db : ev[(size_t)t].h2d0, H));
+            const char* src[3] = {(const char*)in->sw_in, (const char*)in->tc, (const char*)in->pn};
+            for (int k = 0; k < 3; ++k) {
+                if (ahead && k == 1) continue;
+                if (nd > 0)
+                    CU(cudaMemcpy2DAsync(ctx->forcing[s][k].p, (size_t)pitch * fsz, src[k] + (size_t)c0 * fsz, (size_t)istride * fsz,
+                                         (size_t)nct * fsz, (size_t)nd, cudaMemcpyHostToDevice, H));
+                ctx->stats.h2d_bytes += (int64_t)nct * nd * (int64_t)fsz;
+            }
+            if (!ahead) {
+                double* ci = (double*)ctx->cellin[s].p;
+                const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
+                for (int k = 0; k < 5; ++k)
+                    CU(cudaMemcpyAsync(ci + (size_t)k * pitch, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
+                CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6,
+                                     cudaMemcpyHostToDevice, H));
+                CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8,
+                                     (size_t)in->au_layers, cudaMemcpyHostToDevice, H));
+                ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
+            }
+        }
+        CU(cudaEventRecord(ev[(size_t)t].h2d1, H));
+        return SPLASH_OK;
+    }
+
+    // kernel parameters of tile t (no CUDA calls)
+    void setup_params(int64_t t) {
         const size_t fsz = sizeof(FT);
         const int s = (int)(t % kSlots);
         const int64_t c0 = t * tile, nct = cells_of(t);
@@ -1530,12 +1639,13 @@ struct GridJob {
         RunParams& rp = rps[(size_t)t];
         sp = SetupParams{};
         rp = RunParams{};
-        cudaStream_t H = ctx->s_h2d;
         if (in_dev) {
             rp.sw = (const char*)in->sw_in + (size_t)c0 * fsz;
             rp.tc = (const char*)in->tc + (size_t)c0 * fsz;
             rp.pn = (const char*)in->pn + (size_t)c0 * fsz;
-            rp.fpitch = istride;
+            rp.fpitch = rp.tpitch = rp.f1pitch = istride;
+            rp.sw1 = rp.sw;
+            rp.pn1 = rp.pn;
             sp.lat = in->lat + c0;
             sp.elev = in->elev + c0;
             sp.slop = in->slop + c0;
@@ -1545,40 +1655,37 @@ struct GridJob {
             sp.soil_pitch = nc;
             sp.au = in->au + c0;
             sp.au_pitch = nc;
-            CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
         } else {
-            if (t >= kSlots) CU(cudaStreamWaitEvent(H, ev[(size_t)(t - kSlots)].run, 0));  // the slot's previous kernels are done
-            CU(cudaEventRecord(ev[(size_t)t].h2d0, H));
-            const char* src[3] = {(const char*)in->sw_in, (const char*)in->tc, (const char*)in->pn};
-            const void** dst[3] = {&rp.sw, &rp.tc, &rp.pn};
-            for (int k = 0; k < 3; ++k) {
-                if (nd > 0)
-                    CU(cudaMemcpy2DAsync(ctx->forcing[s][k].p, (size_t)pitch * fsz, src[k] + (size_t)c0 * fsz, (size_t)istride * fsz,
-                                         (size_t)nct * fsz, (size_t)nd, cudaMemcpyHostToDevice, H));
-                *dst[k] = ctx->forcing[s][k].p;
-                ctx->stats.h2d_bytes += (int64_t)nct * nd * (int64_t)fsz;
-            }
+            rp.sw = ctx->forcing[s][0].p;
+            rp.pn = ctx->forcing[s][2].p;
             rp.fpitch = pitch;
-            double* ci = (double*)ctx->cellin[s].p;
-            const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
-            for (int k = 0; k < 5; ++k)
-                CU(cudaMemcpyAsync(ci + (size_t)k * pitch, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
-            CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6,
-                                 cudaMemcpyHostToDevice, H));
-            CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8,
-                                 (size_t)in->au_layers, cudaMemcpyHostToDevice, H));
-            ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
+            const double* ci;
+            int64_t cp;
+            if (ahead) {
+                rp.tc = (const char*)a_tc + (size_t)c0 * fsz;
+                rp.sw1 = (const char*)a_sw1 + (size_t)c0 * fsz;
+                rp.pn1 = (const char*)a_pn1 + (size_t)c0 * fsz;
+                rp.tpitch = rp.f1pitch = ncp;
+                ci = a_cellin + c0;
+                cp = ncp;
+            } else {
+                rp.tc = ctx->forcing[s][1].p;
+                rp.sw1 = rp.sw;
+                rp.pn1 = rp.pn;
+                rp.tpitch = rp.f1pitch = pitch;
+                ci = (const double*)ctx->cellin[s].p;
+                cp = pitch;
+            }
             sp.lat = ci;
-            sp.elev = ci + pitch;
-            sp.slop = ci + 2 * pitch;
-            sp.asp = ci + 3 * pitch;
-            sp.resolution = ci + 4 * pitch;
-            sp.soil = ci + 5 * pitch;
-            sp.soil_pitch = pitch;
-            sp.au = ci + 11 * pitch;
-            sp.au_pitch = pitch;
+            sp.elev = ci + cp;
+            sp.slop = ci + 2 * cp;
+            sp.asp = ci + 3 * cp;
+            sp.resolution = ci + 4 * cp;
+            sp.soil = ci + 5 * cp;
+            sp.soil_pitch = cp;
+            sp.au = ci + 11 * cp;
+            sp.au_pitch = cp;
         }
-        CU(cudaEventRecord(ev[(size_t)t].h2d1, H));
 
         // ---- kernel parameters of the tile ----------------------------------------------------------------
         WorkSet& ws = ctx->work[(size_t)work_of(t)];
@@ -1620,7 +1727,6 @@ struct GridJob {
         rp.dpitch = pitch;
         rp.max_spin = max_spin;
         rp.spin_tol = spin_tol;
-        return SPLASH_OK;
     }
 
     // setup, spin-up (first year pair, lock-step rounds), hand-over of the leftovers to the pool
@@ -1629,8 +1735,8 @@ struct GridJob {
         TileEv& e = ev[(size_t)t];
         RunParams& rp = rps[(size_t)t];
         cudaStream_t R = run_stream(t);
-        CU(cudaStreamWaitEvent(R, e.h2d1, 0));
-        if (t >= kSlots && !(in_dev && out_dev)) {
+        CU(cudaStreamWaitEvent(R, ahead ? e.h2da : e.h2d1, 0));
+        if (t >= kSlots && !(in_dev && out_dev) && !ahead) {
             // slot t % kSlots (forcing, work set, output staging) was last used by tile t - kSlots
             CU(cudaStreamWaitEvent(R, ev[(size_t)(t - kSlots)].run, 0));
             if (!out_dev) CU(cudaStreamWaitEvent(R, ev[(size_t)(t - kSlots)].d2h1, 0));
@@ -1639,7 +1745,7 @@ struct GridJob {
         k_tile_begin<<<1, 1, 0, R>>>(rp.ctl, (int)nct);
         k_cell_setup<<<(unsigned)((nct + 127) / 128), 128, 0, R>>>(sps[(size_t)t]);
         CU(cudaGetLastError());
-        k_snow_threshold<FT><<<(unsigned)((nct + 255) / 256), 256, 0, R>>>((const FT*)rp.tc, rp.fpitch, rp.n_days, (int)nct, rp.cc,
+        k_snow_threshold<FT><<<(unsigned)((nct + 255) / 256), 256, 0, R>>>((const FT*)rp.tc, rp.tpitch, rp.n_days, (int)nct, rp.cc,
                                                                             rp.cpitch, rp.diag, rp.dpitch);
         CU(cudaGetLastError());
         launches += 3;
@@ -1677,18 +1783,19 @@ struct GridJob {
         CU(cudaEventRecord(e.kr1, R));
         // ---- leftovers: into the pool (their own streams), or finished here if the pool is full -----------
         k_pool_reserve<<<1, 1, 0, R>>>(rp.ctl, n_rounds, pool.count, pool.cap);
-        k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, n_rounds, (long long)c0);
+        k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, n_rounds, (long long)c0, ahead ? 1 : 3);
         CU(cudaGetLastError());
         launches += 2;
         CU(cudaEventRecord(e.exported, R));
         {
             cudaStream_t Q = ctx->s_pool[t % kPoolStreams];
             CU(cudaStreamWaitEvent(Q, e.exported, 0));
-            RunParams pp = rp;
-            pp.sw = pool.f[0];
+            RunParams& pp = pps[(size_t)t];
+            pp = rp;
+            pp.sw = pp.sw1 = pool.f[0];
             pp.tc = pool.f[1];
-            pp.pn = pool.f[2];
-            pp.fpitch = pool.cap;
+            pp.pn = pp.pn1 = pool.f[2];
+            pp.fpitch = pp.tpitch = pp.f1pitch = pool.cap;
             pp.cc = pool.cc;
             pp.cpitch = pool.cap;
             pp.w = pool.w;
@@ -1709,19 +1816,8 @@ struct GridJob {
             k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, ctx->pool_stage2, 32);
             k_pool_spin<<<(unsigned)ctx->pool_last_ctas, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, ctx->pool_last_lanes);
             CU(cudaEventRecord(e.ps2, Q));
-            launch_list<FT>(pp, monthly, ctx->sm_count * 2, Q);
-            CU(cudaEventRecord(e.pm, Q));
             CU(cudaGetLastError());
-            launches += 5;
-        }
-        {
-            RunParams tp = rp;
-            tp.q_head = &rp.ctl->tail_head;
-            tp.q_end = &rp.ctl->tail_end;
-            tp.q_list = n_rounds ? rp.lists[n_rounds & 1] : nullptr;
-            launch_list<FT>(tp, monthly, ctx->sm_count * 2, R);
-            CU(cudaGetLastError());
-            ++launches;
+            launches += 4;
         }
         return SPLASH_OK;
     }
@@ -1732,6 +1828,35 @@ struct GridJob {
         TileEv& e = ev[(size_t)t];
         RunParams& rp = rps[(size_t)t];
         cudaStream_t R = run_stream(t), D = ctx->s_d2h;
+        if (ahead) {
+            // the tile's whole sw / pn series has to be in its slot, and the slot's previous outputs downloaded
+            CU(cudaStreamWaitEvent(R, e.h2d1, 0));
+            if (t >= kSlots && !out_dev) CU(cudaStreamWaitEvent(R, ev[(size_t)(t - kSlots)].d2h1, 0));
+        }
+        if (!opts.skip_spinup) {
+            const int n_rounds = ctx->n_rounds;
+            // ---- the stragglers' day loop needs their whole forcing columns in the pool -----------------------
+            if (ahead) {
+                k_pool_export<FT><<<(unsigned)(ctx->sm_count * 4), 256, 0, R>>>(rp, pool, n_rounds, (long long)c0, 2);
+                CU(cudaGetLastError());
+                ++launches;
+            }
+            CU(cudaEventRecord(e.exported_b, R));
+            cudaStream_t Q = ctx->s_pool[t % kPoolStreams];
+            CU(cudaStreamWaitEvent(Q, e.exported_b, 0));
+            launch_list<FT>(pps[(size_t)t], monthly, ctx->sm_count * 2, Q);
+            CU(cudaEventRecord(e.pm, Q));
+            CU(cudaGetLastError());
+            ++launches;
+            // ---- leftovers that did not fit the pool: rest of their spin-up and their day loop, in the tile ---
+            RunParams tp = rp;
+            tp.q_head = &rp.ctl->tail_head;
+            tp.q_end = &rp.ctl->tail_end;
+            tp.q_list = n_rounds ? rp.lists[n_rounds & 1] : nullptr;
+            launch_list<FT>(tp, monthly, ctx->sm_count * 2, R);
+            CU(cudaGetLastError());
+            ++launches;
+        }
         CU(cudaEventRecord(e.kb0, R));
         launch_bulk<FT>(rp, monthly, R);
         CU(cudaGetLastError());
@@ -1830,6 +1955,7 @@ struct GridJob {
         if (int rc = allocate()) return rc;
         CU(cudaEventRecord(ev_begin, ctx->s_h2d));
         for (auto s : ctx->s_run) CU(cudaStreamWaitEvent(s, ev_begin, 0));  // (idle streams included: harmless)
+        for (int64_t t = 0; t < n_tiles; ++t) setup_params(t);
         if (in_dev && out_dev && ctx->two_pass) {
             // resident data: every tile's spin-up first, so that the stragglers (up to 1000 sequential year
             // passes) start as early as possible and run beside the daily integration of all tiles
@@ -1839,6 +1965,17 @@ struct GridJob {
             }
             for (int64_t t = 0; t < n_tiles; ++t)
                 if (int rc = enqueue_main(t)) return rc;
+        } else if (ahead) {
+            // host-fed: the spin-up data of every tile goes up first (40 % of the bytes of a 10-year call), all
+            // tiles spin up while the rest of the forcing follows tile by tile through the slots
+            for (int64_t t = 0; t < n_tiles; ++t)
+                if (int rc = enqueue_h2d_ahead(t)) return rc;
+            for (int64_t t = 0; t < n_tiles; ++t)
+                if (int rc = enqueue_spin(t)) return rc;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                if (int rc = enqueue_h2d(t)) return rc;   // waits for the slot (tile t - kSlots enqueued below)
+                if (int rc = enqueue_main(t)) return rc;
+            }
         } else {
             for (int64_t t = 0; t < n_tiles; ++t) {
                 if (int rc = enqueue_h2d(t)) return rc;
@@ -1876,7 +2013,12 @@ struct GridJob {
             st.pool_max_passes = std::max<int64_t>(st.pool_max_passes, (int64_t)c.max_chain);
             const TileEv& e = ev[(size_t)t];
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, e.h2d0, e.h2d1) == cudaSuccess) st.h2d_ms += ms;
+            if (ahead) {
+                if (cudaEventElapsedTime(&ms, e.h2d0, e.h2da) == cudaSuccess) st.h2d_ms += ms;
+                if (cudaEventElapsedTime(&ms, e.h2db, e.h2d1) == cudaSuccess) st.h2d_ms += ms;
+            } else if (cudaEventElapsedTime(&ms, e.h2d0, e.h2d1) == cudaSuccess) {
+                st.h2d_ms += ms;
+            }
             if (cudaEventElapsedTime(&ms, e.k0, e.kf0) == cudaSuccess) st.setup_ms += ms;
             if (cudaEventElapsedTime(&ms, e.kf0, e.kf1) == cudaSuccess) st.first_ms += ms;
             if (cudaEventElapsedTime(&ms, e.kf1, e.kr1) == cudaSuccess) st.rounds_ms += ms;
