@@ -101,7 +101,48 @@ extern "C" SEXP splash_release_R(void) {
     return R_NilValue;
 }
 
+// .Call("splash_unswc_grid_R", soil, wn, uns_depth, device)
+//   soil : numeric matrix [cells x 6];  wn : numeric matrix [cells x layers] (raster::getValues of the wn brick)
+//   returns list(theta_i, wtd, w_z, Se), each [cells x layers]: the four overlay() passes of unSWC.grid
+//   (reference R/unsSWC.grid.R:96-139), which keeps its netCDF writing
+extern "C" SEXP splash_unswc_grid_R(SEXP soil, SEXP wn, SEXP uns_depth, SEXP device) {
+    const R_xlen_t nc = XLENGTH(soil) / 6;
+    const R_xlen_t nl = nc ? XLENGTH(wn) / nc : 0;
+    splash_unswc_in in = {0};
+    in.n_cells = nc;
+    in.n_layers = nl;
+    in.soil = REAL(soil);
+    in.wn = REAL(wn);
+    in.uns_depth = Rf_asReal(uns_depth);
+    in.mem_kind = SPLASH_MEM_HOST;
+    const char* names[4] = {"theta_i", "wtd", "w_z", "Se"};
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 4)), nm = PROTECT(Rf_allocVector(STRSXP, 4));
+    double* ptr[4];
+    for (int k = 0; k < 4; ++k) {
+        SEXP m = PROTECT(Rf_allocMatrix(REALSXP, (int)nc, (int)nl));
+        SET_VECTOR_ELT(res, k, m);
+        SET_STRING_ELT(nm, k, Rf_mkChar(names[k]));
+        ptr[k] = REAL(m);
+        UNPROTECT(1);
+    }
+    Rf_setAttrib(res, R_NamesSymbol, nm);
+    splash_unswc_out out = {0};
+    out.theta_i = ptr[0];
+    out.wtd = ptr[1];
+    out.w_z = ptr[2];
+    out.se = ptr[3];
+    out.mem_kind = SPLASH_MEM_HOST;
+    splash_ctx* ctx = get_ctx(Rf_asInteger(device));
+    if (splash_unswc_grid_run(ctx, &in, &out) != SPLASH_OK) {
+        UNPROTECT(2);
+        Rf_error("libsplash_cuda: %s", splash_last_error(ctx));
+    }
+    UNPROTECT(2);
+    return res;
+}
+
 static const R_CallMethodDef call_methods[] = {{"splash_grid_run_R", (DL_FUNC)&splash_grid_run_R, 15},
+                                               {"splash_unswc_grid_R", (DL_FUNC)&splash_unswc_grid_R, 4},
                                                {"splash_release_R", (DL_FUNC)&splash_release_R, 0},
                                                {NULL, NULL, 0}};
 
