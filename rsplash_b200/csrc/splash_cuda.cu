@@ -1163,6 +1163,8 @@ extern "C" {
 
 int splash_abi_version(void) { return SPLASH_ABI_VERSION; }
 
+static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& prop);
+
 int splash_ctx_create(int device, splash_ctx** out_ctx) {
     splash_ctx* ctx = nullptr;
     if (!out_ctx) return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_ctx_create: out_ctx is NULL");
@@ -1187,6 +1189,17 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
         return fail(nullptr, SPLASH_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     ctx = new splash_ctx();
+    const int rc = ctx_create_impl(device, ctx, prop);
+    if (rc != SPLASH_OK) {  // the message must outlive the context
+        g_create_err = ctx->err;
+        splash_ctx_destroy(ctx);
+        return rc;
+    }
+    *out_ctx = ctx;
+    return SPLASH_OK;
+}
+
+static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& prop) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("SPLASH_RUN_STREAMS")) ctx->n_run_streams = std::max(1, std::min(kRunStreams, atoi(v)));
@@ -1215,7 +1228,6 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));  // stragglers first
     CU(prepare_kernels<double>());
     CU(prepare_kernels<float>());
-    *out_ctx = ctx;
     return SPLASH_OK;
 }
 
