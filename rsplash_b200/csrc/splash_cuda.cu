@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(256) k_snow_threshold(const FT* __restrict__ t
 #pragma unroll 4
     for (int d = 0; d < n_days; ++d) {
         const double t = ld_stream(col + (int64_t)d * fpitch);
-        const double p = snow_prob(ccg, t);
-        if (isnan(p)) {
+        const int snowy = snow_class(ccg, t);
+        if (snowy < 0) {
             any_na = true;
-        } else if (p >= 0.5) {
+        } else if (snowy) {
             ++n_snow;
             if (t > Tt) Tt = t;
         }

@@ -10,7 +10,7 @@
 //                     EVAP::elv2pres (src/EVAP.cpp:319-336), SOLAR tau_o (src/SOLAR.cpp:170)
 //   lateral_consts()  the terms of run_one_day that depend on `cellout`, which R overwrites with
 //                     the aridity index between the two spin-ups (R/splash.point.R:150)
-//   snow_prob_z()     snowfall_prob, R/splash.point.R:560-578
+//   snow_class()      snowfall_prob, R/splash.point.R:560-578 (NA / p_snow >= 0.5 / not)
 //   splash_day()      one day: snow partition (R/splash.point.R:120-128,547-555), then
 //                     SOLAR::calculate_daily_fluxes (src/SOLAR.cpp:129-255),
 //                     EVAP::calculate_daily_fluxes (src/EVAP.cpp:100-263),
@@ -404,10 +404,17 @@ __device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, 
         return column_transmittance_core<M>(cc, sm, ksat_visc);
 }
 
-// snowfall_prob's exponent, R/splash.point.R:576
+// snowfall_prob, R/splash.point.R:576: p_snow = 1 / (1 + exp(z)).  The path only ever asks whether p_snow is NA
+// and whether p_snow >= 0.5 (:122,124).  p_snow >= 0.5 <=> exp(z) <= 1 <=> z <= 0, so away from z == 0 the sign of
+// the exponent decides and no exp / division is needed; within 1e-9 of zero the expression is evaluated as
+// written.  Returns -1 (NA), 1 (snow-probable day) or 0.
 template <class CC>
-__device__ __forceinline__ double snow_prob(const CC& cc, double tc) {
-    return SPLASH_FDIV(1.0, 1 + f_exp(-0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K)));
+__device__ __forceinline__ int snow_class(const CC& cc, double tc) {
+    const double z = -0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K);
+    if (isnan(z)) return -1;
+    if (z < -1e-9) return 1;
+    if (z > 1e-9) return 0;
+    return (1 / (1 + exp(z)) >= 0.5) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,11 +451,11 @@ template <class CC>
 __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
                                             double pn, DayPre& q) {
     // ---- snow partition, R/splash.point.R:120-128 with frain_func :547-555 ------------------------
-    const double p_snow = snow_prob(cc, tc);
+    const int snowy = snow_class(cc, tc);
     double f_rain;
-    if (isnan(p_snow)) {
-        f_rain = p_snow;  // ifelse(NA, ., .) is NA
-    } else if (p_snow >= 0.5) {
+    if (snowy < 0) {
+        f_rain = nan("");  // ifelse(NA, ., .) is NA
+    } else if (snowy) {
         const double Tt = cc(C_TT);
         const double Ttm = Tt + (Tt * mt.s1[dt.month]);
         const double x = SPLASH_FDIV(tc - Ttm, mt.trm14[dt.month]);
