@@ -940,6 +940,11 @@ __global__ void k_debug_math(int op, int64_t n, const double* x, double* y) {
     y[i] = op == 0 ? f_exp(v) : op == 1 ? f_log(v) : op == 2 ? f_acos(v) : f_sin(v);
 }
 
+__global__ void k_init_tables() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kSnowAgeTab) g_snow_age_tab[i] = snow_age_factor_formula((double)i);
+}
+
 __global__ void k_tile_begin(TileCtl* ctl, int n_cells) {  // (the control blocks are zeroed once per call)
     ctl->cnt[0] = (unsigned long long)n_cells;
 }
@@ -1226,6 +1231,9 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     for (auto& s : ctx->s_run) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_lo));
     for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));  // stragglers first
+    k_init_tables<<<(kSnowAgeTab + 255) / 256, 256>>>();
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
     CU(prepare_kernels<double>());
     CU(prepare_kernels<float>());
     return SPLASH_OK;

@@ -159,6 +159,30 @@ __device__ __noinline__ double f_acos(double x) { return acos(x); }
 __device__ __noinline__ double f_sin(double x) { return sin(x); }
 #endif
 
+// Snow-age factor of the albedo, SOLAR.cpp:208: exp(-0.895189 * nd).  nd counts the days since the last snowfall
+// (0, 1, 2, ...), so the factor only takes the values of a table, which k_init_tables fills with the very
+// function the day step would call (bit-identical); beyond the table the factor has underflowed to exactly 0.
+constexpr int kSnowAgeTab = 1024;
+__device__ double g_snow_age_tab[kSnowAgeTab];
+
+__device__ __forceinline__ double snow_age_factor_formula(double nd) { return f_exp(-0.895189 * nd); }
+
+__device__ __forceinline__ double snow_age_factor(double nd) {
+#if SPLASH_LEVEL >= 1
+    if (nd >= 0.0 && nd < (double)kSnowAgeTab) {
+        const int i = (int)nd;
+        if ((double)i == nd) return g_snow_age_tab[i];
+    }
+#endif
+    return snow_age_factor_formula(nd);
+}
+
+// Hour angle h = acos(x) (degrees) together with sin(h): the reference evaluates sin(h * pir) after
+// h = acos(x) / pir; level 1 takes sin(acos(x)) = sqrt((1 - x)(1 + x)) instead (accurate to ~1.5 ulp for
+// every |x| < 1, no cancellation), and the reference's own values at the clamps: sin(0) = 0 and
+// sin(180 * pir) = sin(fl(pi)) = 1.2246467991473532e-16.
+#define SPLASH_SIN_180 1.2246467991473532e-16
+
 // How the state half of the day step reaches its transcendentals.  MathShared: calls of the shared
 // out-of-line copies (the throughput kernels, where 16 warps per SM share the instruction cache).
 // MathInline: the same algorithms expanded in place -- no call, no argument shuffling -- for the
@@ -490,6 +514,20 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     const double rv = b;
     double hs;
     const double ruv = SPLASH_FDIV(ru, rv);
+#if SPLASH_L1_POW
+    double sin_hs;
+    if (ruv >= 1.0) {
+        hs = 180.0;
+        sin_hs = SPLASH_SIN_180;
+    } else if (ruv <= -1.0) {
+        hs = 0.0;
+        sin_hs = 0.0;
+    } else {
+        const double x = -1.0 * ruv;
+        hs = SPLASH_TO_DEG(f_acos(x));
+        sin_hs = sqrt((1.0 - x) * (1.0 + x));
+    }
+#else
     if (ruv >= 1.0) {
         hs = 180.0;
     } else if (ruv <= -1.0) {
@@ -500,6 +538,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         hs = SPLASH_TO_DEG(hs);
     }
     const double sin_hs = f_sin(hs * kpir);
+#endif
     double ra_d = (86400.0 / kPI) * dt.dr * kGsc;
     ra_d *= (ru * hs * kpir + rv * sin_hs);
     const double tau_o = cc(C_TAU_O);
@@ -602,7 +641,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 
     // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:208-255 ------------------------------------------
     const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
-    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * M::exp(-0.895189 * nd));
+    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * snow_age_factor(nd));
     const double sfc = SPLASH_FDIV(snow, 140.0 + snow);
     const double alb_v = kalb_sw - 0.17 * sw;
     const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
@@ -614,6 +653,19 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     }
     double hn;
     const double qn = SPLASH_FDIV(rnl - rw * ru, rw * rv);
+#if SPLASH_L1_POW
+    double sin_hn;
+    if (qn >= 1.0) {
+        hn = 0;
+        sin_hn = 0.0;
+    } else if (qn <= -1.0) {
+        hn = 180.0;
+        sin_hn = SPLASH_SIN_180;
+    } else {
+        hn = SPLASH_TO_DEG(M::acos(qn));
+        sin_hn = sqrt((1.0 - qn) * (1.0 + qn));
+    }
+#else
     if (qn >= 1.0) {
         hn = 0;
     } else if (qn <= -1.0) {
@@ -623,6 +675,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         hn = SPLASH_TO_DEG(hn);
     }
     const double sin_hn = M::sin(hn * kpir);
+#endif
     double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
     rn_d *= (86400.0 / kPI);
     double rnn_d = rw * rv * (sin_hs - sin_hn);
@@ -643,6 +696,19 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     }
     const double cos_hi = SPLASH_FDIV(swp, rw * rv * rx) + SPLASH_FDIV(rnl, rw * rv) - q.ruv;  // ru/rv: same operands as in day_forcing
     double hi;
+#if SPLASH_L1_POW
+    double sin_hi;
+    if (cos_hi >= 1.0) {
+        hi = 0.0;
+        sin_hi = 0.0;
+    } else if (cos_hi <= -1.0) {
+        hi = 180.0;
+        sin_hi = SPLASH_SIN_180;
+    } else {
+        hi = SPLASH_TO_DEG(M::acos(cos_hi));
+        sin_hi = sqrt((1.0 - cos_hi) * (1.0 + cos_hi));
+    }
+#else
     if (cos_hi >= 1.0) {
         hi = 0.0;
     } else if (cos_hi <= -1.0) {
@@ -651,6 +717,8 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         hi = M::acos(cos_hi);
         hi = SPLASH_TO_DEG(hi);
     }
+    const double sin_hi = M::sin(hi * kpir);
+#endif
     double snowmelt_tot;
     if (tc >= 3.0) {
         snowmelt_tot = cxx_min(snow, SPLASH_FDIV(rn_d, pw * kkfus) * 1000.0);
@@ -662,7 +730,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
     melt_enrg += SPLASH_FDIV(SPLASH_DIVC(sublimation, 1000.0), econ);
     double aet_d = swp * hi * kpir;
-    aet_d += rx * rw * rv * (sin_hn - M::sin(hi * kpir));
+    aet_d += rx * rw * rv * (sin_hn - sin_hi);
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
     aet_d *= (24.0 / kPI);
     aet_d -= (melt_enrg * econ * 1000.0);
