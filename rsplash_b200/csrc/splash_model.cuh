@@ -468,6 +468,11 @@ struct DayPre {
     double tc;
     double s, g, econ, pw, eet_k, rx; // EVAP.cpp:110-145
     double ksat_visc;                 // SPLASH.cpp:1260
+#if SPLASH_L1_RECIP
+    // level 1: reciprocals of forcing-only denominators of the state half (computed once per day here; for a
+    // straggler once per spin-up year, in the pool's table)
+    double inv_rw_den, inv_rx, inv_econ, inv_pwk, inv_k24;
+#endif
 };
 constexpr int kDayPreDoubles = sizeof(DayPre) / sizeof(double);
 
@@ -605,6 +610,13 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.eet_k = (1.0e3) * SPLASH_FDIV(s, lv * pw * (s + 0.24 * g));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
     q.rx = (3.6e6) * econ;
     q.ksat_visc = cc(C_INTPERM) * SPLASH_FDIV(pw * kG, visc) * 3.6;  // SPLASH.cpp:1260
+#if SPLASH_L1_RECIP
+    q.inv_rw_den = SPLASH_FDIV(1.0, q.rw_den);
+    q.inv_rx = SPLASH_FDIV(1.0, q.rx);
+    q.inv_econ = SPLASH_FDIV(1.0, econ);
+    q.inv_pwk = SPLASH_FDIV(1.0, pw * kkfus);
+    q.inv_k24 = SPLASH_FDIV(1.0, q.ksat_visc * 24);
+#endif
 }
 
 template <class M = MathShared, class CC>
@@ -649,10 +661,19 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     if (q.rw_dark != 0.0) {
         rw = (1.0 - alb) * q.tau * q.dr * kGsc;
     } else {
+#if SPLASH_L1_RECIP
+        rw = (1.0 - alb) * (q.r_in) * q.inv_rw_den;
+#else
         rw = SPLASH_FDIV((1.0 - alb) * (q.r_in), q.rw_den);
+#endif
     }
     double hn;
+#if SPLASH_L1_RECIP
+    const double inv_rwrv = SPLASH_FDIV(1.0, rw * rv);  // shared by qn and cos_hi
+    const double qn = (rnl - rw * ru) * inv_rwrv;
+#else
     const double qn = SPLASH_FDIV(rnl - rw * ru, rw * rv);
+#endif
 #if SPLASH_L1_POW
     double sin_hn;
     if (qn >= 1.0) {
@@ -688,13 +709,22 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
     const double eet_d = q.eet_k * rn_d;
     const double pet_max = rx * ((rw * (ru + rv)) - rnl);
+#if SPLASH_L1_RECIP
+    // EF = 1 / (g / (sw s) + 1) = sw s / (g + sw s): one division; sw == 0 gives 0 either way
+    const double EF = SPLASH_FDIV(sw * s, g + sw * s);
+#else
     const double B_r = SPLASH_FDIV(g, sw * s);
     const double EF = SPLASH_FDIV(1.0, B_r + 1.0);
+#endif
     double swp = pet_max * EF;
     if (swp < 0.0 || isnan(swp)) {
         swp = 0.0;
     }
+#if SPLASH_L1_RECIP
+    const double cos_hi = swp * inv_rwrv * q.inv_rx + rnl * inv_rwrv - q.ruv;
+#else
     const double cos_hi = SPLASH_FDIV(swp, rw * rv * rx) + SPLASH_FDIV(rnl, rw * rv) - q.ruv;  // ru/rv: same operands as in day_forcing
+#endif
     double hi;
 #if SPLASH_L1_POW
     double sin_hi;
@@ -721,14 +751,22 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 #endif
     double snowmelt_tot;
     if (tc >= 3.0) {
+#if SPLASH_L1_RECIP
+        snowmelt_tot = cxx_min(snow, (rn_d * q.inv_pwk) * 1000.0);
+#else
         snowmelt_tot = cxx_min(snow, SPLASH_FDIV(rn_d, pw * kkfus) * 1000.0);
+#endif
     } else {
         snowmelt_tot = 0.0;
     }
     double melt_enrg = SPLASH_DIVC(snowmelt_tot, 1000.0) * pw * kkfus;
     const double AE = rn_d - melt_enrg;
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
+#if SPLASH_L1_RECIP
+    melt_enrg += SPLASH_DIVC(sublimation, 1000.0) * q.inv_econ;
+#else
     melt_enrg += SPLASH_FDIV(SPLASH_DIVC(sublimation, 1000.0), econ);
+#endif
     double aet_d = swp * hi * kpir;
     aet_d += rx * rw * rv * (sin_hn - sin_hi);
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
@@ -807,7 +845,11 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double Kunsat = Ksat_visc * pow((theta_m / theta_s), cc(C_KUEXP));
 #endif
     const double hyd_grad_in = cc(C_TAN_S);
+#if SPLASH_L1_RECIP
+    const double hyd_grad_z = infi * q.inv_k24 - 1.0;
+#else
     const double hyd_grad_z = SPLASH_FDIV(infi, Ksat_visc * 24) - 1.0;
+#endif
     const double hyd_grad_out = sqrt((hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in));
 
     // ---- 5.2.1 recession constant, :1303-1326 ------------------------------------------------------
