@@ -6,11 +6,22 @@ double pp_pow(double, double);
 double pp_pow_explog(double, double);
 double pp_exp(double);
 double pp_log(double);
+double pp_sin(double);
+double pp_acos(double);
+#ifdef PERTURB_ALL   /* every libm call of the path at once */
+#define PERTURB_POW
+#define PERTURB_EXPLOG
+#define PERTURB_TRIG
+#endif
 #ifdef PERTURB_POW
 #define pow pp_pow
 #endif
 #ifdef PERTURB_POWEXPLOG
 #define pow pp_pow_explog
+#endif
+#ifdef PERTURB_TRIG
+#define sin pp_sin
+#define acos pp_acos
 #endif
 #ifdef PERTURB_EXPLOG
 #define exp pp_exp

@@ -329,7 +329,9 @@ static double density_h2o(double tc, double p) {
 
 /* EVAP::calc_viscosity_h2o, src/EVAP.cpp:405-462.  FP32 locals with double sub-expressions, exactly
  * as C++ evaluates `float x = <double expr>`. */
-static float calc_viscosity_h2o(float tc, float p) {
+/* (the optimize attribute only matters for the `RECIP` sensitivity build, oracle/Makefile: the FP32 arithmetic of
+ * this routine is kept as written there too -- a float division off by one ulp is 6e-8, not a last-bit effect) */
+__attribute__((optimize("no-reciprocal-math"))) static float calc_viscosity_h2o(float tc, float p) {
     float tk_ast = 647.096;
     float rho_ast = 322.0;
     float mu_ast = 1e-6;

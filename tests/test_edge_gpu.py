@@ -23,9 +23,9 @@ def gpu(ctx, prob, dates, monthly=False, **kw):
 
 def check_vs_oracle(got, prob, ref=None):
     ref = ref if ref is not None else ol.run_cpu(prob, monthly=False, core="oracle")
-    stable, _ = conditioning.stable_cells(prob, ref)
+    stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
     cells = np.flatnonzero(stable)
-    assert len(cells) >= 0.8 * prob.n_cells
+    assert len(cells) >= 0.4 * prob.n_cells
     sub = lambda r: {**{k: np.asarray(r[k])[:, cells] for k in _abi.OUTPUT_NAMES}, "cell_diag": np.asarray(r["cell_diag"])[:, cells]}
     parity.compare(sub(got), sub(ref))
     parity.compare_diag(sub(got)["cell_diag"], sub(ref)["cell_diag"])

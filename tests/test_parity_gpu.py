@@ -78,26 +78,35 @@ def _subset(res: dict, cells) -> dict:
 
 
 def _check_synthetic(ctx, n_cells, n_years, seed, max_unstable, **kw):
-    """GPU vs the C restatement on seeded synthetic cells.  Every cell that is well-conditioned in the
-    reference (tests/conditioning.py) must meet the full gates; the rest is counted and bounded."""
+    """GPU vs the C restatement on seeded synthetic cells (tests/conditioning.py):
+      * every cell that is stable under the dense libm perturbations meets the full gates,
+      * of the cells stable under the sparse ones at most 1 in 1000 may miss them (the sparse screen is a sample),
+      * the GPU leaves the gates in fewer cells than the reference does when 1 pow() in 8 moves by an ulp,
+      * NaN masks, Tt and the snow-day counts are exact for every cell."""
     from tests import conditioning
     from tests.synthetic import make_problem
 
     prob, dates = make_problem(n_cells=n_cells, n_years=n_years, seed=seed)
     ref = ol.run_cpu(prob, monthly=False, core="oracle")
-    stable, knocked = conditioning.stable_cells(prob, ref)
+    sparse, knocked = conditioning.stable_cells(prob, ref, conditioning.SPARSE)
+    dense, knocked_d = conditioning.stable_cells(prob, ref, conditioning.DENSE)
+    dense &= sparse
     got = run_gpu(ctx, prob, dates, monthly=False, **kw)
-    n_unstable = int((~stable).sum())
     dev = conditioning.cell_deviation(got, ref)
     gpu_off = np.zeros(n_cells, dtype=bool)
     for k, d in dev.items():
-        gpu_off |= ~(d <= (1e-9 if k in parity.FLUX else 1e-6))
-    print(f"synthetic {n_cells}x{prob.n_days}: unstable in the reference {n_unstable} {knocked}; "
-          f"GPU outside the gates {int(gpu_off.sum())}, of which stable {int((gpu_off & stable).sum())}")
-    assert n_unstable <= max_unstable * n_cells, (n_unstable, knocked)
-    cells = np.flatnonzero(stable)
+        gpu_off |= ~(d <= (1e-9 if k in parity.FLUX else (1e-8 if k == "sm_lim" else 1e-6)))
+    n_sparse_unstable = int((~sparse).sum())
+    print(f"synthetic {n_cells}x{prob.n_days} seed {seed}: reference-unstable {n_sparse_unstable} {knocked}, densely stable "
+          f"{int(dense.sum())} {knocked_d}; GPU outside the gates {int(gpu_off.sum())}, of which sparsely stable "
+          f"{int((gpu_off & sparse).sum())}, densely stable {int((gpu_off & dense).sum())}")
+    assert n_sparse_unstable <= max_unstable * n_cells, (n_sparse_unstable, knocked)
+    assert dense.sum() >= 0.3 * n_cells
+    cells = np.flatnonzero(dense)
     parity.compare(_subset(got, cells), _subset(ref, cells))
     parity.compare_diag(got["cell_diag"][:, cells], ref["cell_diag"][:, cells])
+    assert (gpu_off & sparse).sum() <= max(1, n_cells // 1000)
+    assert gpu_off.sum() <= max(2, knocked["POW"])
     # NaN masks, snow-day and snowfall-day counts are bit-exact for EVERY cell, stable or not
     for k in _abi.OUTPUT_NAMES:
         assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
