@@ -788,7 +788,11 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 #if SPLASH_L1_POW
         // head/bp = (bp/u + 10)/bp = 1/u + 10/bp with u = x^(1/lambda); 1/u = M::exp(-M::log(x)/lambda)
         const double lx = M::log(SPLASH_DIV_DTH(theta_mean - theta_r));
-        const double head = M::exp(-(cc(C_ILAM) * lx)) + cc(C_TEN_BP);
+        const double inv_u = M::exp(-(cc(C_ILAM) * lx));
+        double head = inv_u + cc(C_TEN_BP);
+        // the reference forms bp/u first (:1945), which overflows to -inf once |bp|/u > DBL_MAX (dry soil with a
+        // tiny lambda: u = x^(1/lambda) ~ 1e-306); head/bp is then +inf and theta_BC collapses onto theta_r
+        if (inv_u > fabs(cc(C_TEN_BP)) * 1.7976931348623157e307) head = INFINITY;
         double theta_BC = cc(C_DTH) * M::exp(cc(C_NLAM) * M::log(head)) + theta_r;
 #else
         const double bp = cc(C_BP10);
@@ -858,7 +862,10 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
     const double Q_qs = SPLASH_DIVC(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS), 1000.0);
 #if SPLASH_L1_RECIP
-    const double Kb = M::exp((Q_q0 - Q_qs) * cc(C_INV_DENKB));
+    // 5.7 takes log(Kb) back (:1470): on gentle slopes the exponent is ~1e-8 and every bit of Kb counts.  There
+    // 1 + z + z^2/2 rounds to the correctly rounded exp(z) (as glibc's exp does) with probability 1 - |z|.
+    const double z_kb = (Q_q0 - Q_qs) * cc(C_INV_DENKB);
+    const double Kb = (fabs(z_kb) < 0x1p-20) ? 1.0 + fma(0.5 * z_kb, z_kb, z_kb) : M::exp(z_kb);
 #else
     const double Kb = M::exp((Q_q0 - Q_qs) / cc(C_DENKB));
 #endif

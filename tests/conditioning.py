@@ -90,6 +90,11 @@ def stable_cells(prob: ol.GridProblem, base: dict | None = None, variants=SPARSE
         got = run_variant(v, prob)
         dev = cell_deviation(got, base)
         bad = got["cell_diag"][ip] != base["cell_diag"][ip]
+        # the float diagnostics (the aridity index of the first spin-up pass above all) must hold still as well
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a, b = got["cell_diag"], base["cell_diag"]
+            rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+        bad |= (np.nan_to_num(rel, nan=0.0, posinf=0.0) > 1e-13).any(0)
         for k, d in dev.items():
             lim = 1e-10 if k in ("pet", "netr", "aet", "cond") else (1e-9 if k == "sm_lim" else 1e-7)
             bad |= ~(d <= lim)

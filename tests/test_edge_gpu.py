@@ -133,6 +133,21 @@ def test_pool_overflow_path_gives_the_same_bits():
         assert np.array_equal(base[k], got[k], equal_nan=True), k
 
 
+def test_tiny_lambda_on_dry_soil(ctx):
+    """Clay-rich gravelly soils give a pore-size index lambda ~ 1e-3.  On dry soil moist_surf's x^(1/lambda)
+    (SPLASH.cpp:1943-1947) then drops below |bub_press|/DBL_MAX and the reference's bp/u overflows, which puts the
+    surface moisture on theta_r.  The level-1 arithmetic evaluates 1/u directly and has to reproduce that."""
+    prob, dates = make_problem(n_cells=400, n_years=1, seed=5)
+    rng = np.random.default_rng(1)
+    n = prob.n_cells
+    for row, (lo, hi) in enumerate([(5, 20), (38, 46), (1, 3), (20, 40), (1.45, 1.7)]):
+        prob.soil[row] = rng.uniform(lo, hi, n).astype(np.float32)
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    lam = ref["cell_diag"][_abi.DIAG_NAMES.index("lambda")]
+    assert (lam < 0.01).sum() >= 20
+    check_vs_oracle(gpu(ctx, prob, dates), prob, ref)
+
+
 def test_one_cell_and_one_day(ctx):
     prob, dates = make_problem(n_cells=1, n_years=1, seed=12)
     one = ol.GridProblem(prob.year[:1], prob.doy[:1], prob.month[:1], prob.sw_in[:1], prob.tc[:1], prob.pn[:1], prob.lat, prob.elev,
