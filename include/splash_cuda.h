@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SPLASH_ABI_VERSION 3
+#define SPLASH_ABI_VERSION 4
 #define SPLASH_NSTATE 6
 
 /* status codes */
@@ -220,6 +220,30 @@ typedef struct splash_unswc_out {
 } splash_unswc_out;
 
 int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_unswc_out* out);
+
+/* ---- monthly -> daily forcing: the deterministic half of splash.point's step 01 (R/splash.point.R:66-86) ----
+ * When the forcing is monthly, splash.point interpolates air temperature and shortwave radiation onto the daily
+ * axis with stats::approx(time_index_month, x, time_index, method = "linear", rule = 2)$y (:77, :83): knots at the
+ * first day of each month, NA months dropped, the end values held outside the knots, and an all-NA series when
+ * fewer than two months are present (:75-76, :81-82).  This entry does that for a block of cells on the device,
+ * so that monthly grids (the CRU example of the package) cross the PCIe bus as monthly data and the daily series
+ * exist only in HBM, in the layout splash_grid_in takes (pass the result as device forcing).  Precipitation goes
+ * through month2day_rain (:460-516), which draws from rgamma and stays with the caller. */
+typedef struct splash_m2d_in {
+    int64_t n_cells;
+    int64_t n_months;
+    int64_t n_days;
+    int64_t in_stride;          /* elements between consecutive months of `monthly`; 0 means n_cells */
+    int64_t out_stride;         /* elements between consecutive days of the output; 0 means n_cells */
+    const int32_t* month_start; /* [n_months] HOST: 0-based index on the daily axis of each month's first day
+                                 * (time_index_month - time_index[1]); strictly increasing */
+    const double* monthly;      /* [n_months*in_stride] month-major, cells contiguous */
+    int32_t mem_kind;           /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE, for `monthly` and the output alike */
+    int32_t out_f32;            /* 0: the output is double[]; 1: float[] (the f32 forcing layout of splash_grid_in) */
+} splash_m2d_in;
+
+/* daily_out: [n_days*out_stride] double or float according to in->out_f32. */
+int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* daily_out);
 
 /* Diagnostic (used by tests/test_math_gpu.py, not by the R glue): apply one of the day step's
  * transcendental functions to a host array on the device.  op: 0 exp, 1 log, 2 acos, 3 sin (hour

@@ -971,6 +971,42 @@ static int cond_le(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a
 static int cond_gt(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a > b); }
 static int cond_lt(double a, double b) { return (isnan(a) || isnan(b)) ? -1 : (a < b); }
 
+/* stats::approx(x, y, xout, method = "linear", rule = 2) for one series (see splash_oracle.h).
+ * x[n], y[n]: the knots left after the NA pairs were dropped, x increasing. */
+static double r_approx1_linear(double v, const double* x, const double* y, long long n) {
+    if (n == 0) return NAN;
+    long long i = 0, j = n - 1;
+    if (v < x[i]) return y[0];     /* rule = 2: ylow = y[1] */
+    if (v > x[j]) return y[n - 1]; /* yhigh = y[n] */
+    while (i < j - 1) {            /* bisection: x[i] <= v <= x[j] */
+        long long ij = (i + j) / 2;
+        if (v < x[ij]) j = ij; else i = ij;
+    }
+    if (v == x[j]) return y[j];
+    if (v == x[i]) return y[i];
+    return y[i] + (y[j] - y[i]) * ((v - x[i]) / (x[j] - x[i]));
+}
+
+void splash_oracle_month2day_linear(long long n_cells, long long n_months, long long n_days, const int* month_start,
+                                    const double* monthly, double* daily) {
+    double* x = (double*)malloc(sizeof(double) * (size_t)(2 * n_months + 2));
+    double* y = x + n_months + 1;
+    for (long long c = 0; c < n_cells; c++) {
+        long long n = 0;
+        for (long long m = 0; m < n_months; m++) {
+            double v = monthly[m * n_cells + c];
+            if (!isnan(v)) { /* regularize.values(na.rm = TRUE) */
+                x[n] = (double)month_start[m];
+                y[n] = v;
+                n++;
+            }
+        }
+        for (long long d = 0; d < n_days; d++) /* sum(!is.na(tc)) < 2 -> rep(NA, ...), R/splash.point.R:75-76 */
+            daily[d * n_cells + c] = (n < 2) ? NAN : r_approx1_linear((double)d, x, y, n);
+    }
+    free(x);
+}
+
 /* calcwtd / the first lines of UnsWater, R/unsSWC.grid.R:49-50,113-115 */
 static double unswc_wtd(double psi_m, double totdepth, double bub_press) {
     double wtdini = (bub_press - psi_m) / 1000;

@@ -70,6 +70,16 @@ void splash_oracle_soil_hydro(double sand, double clay, double OM, double fgrave
 void splash_oracle_unswc_grid(long long n_cells, long long n_layers, const double* soil, const double* wn, double uns_depth,
                               double* theta_i, double* wtd, double* w_z, double* se);
 
+/* Monthly -> daily interpolation of tc and sw_in when the forcing is monthly (R/splash.point.R:74-84):
+ * stats::approx(time_index_month, x, time_index, method = "linear", rule = 2)$y, or all NA when fewer than two
+ * months are non-NA.  stats::approx is base R (not in /root/reference; any R >= 3.x): regularize.values() drops the
+ * pairs with NA, R_approxfun's approx1() brackets each day by bisection and interpolates linearly; rule = 2 holds
+ * y[1] / y[n] outside the knots.  PARITY UNPINNED: restated from R's published algorithm, never run against R.
+ * monthly [n_months*n_cells] month-major, month_start[n_months] = day index of each month's first day,
+ * daily [n_days*n_cells]. */
+void splash_oracle_month2day_linear(long long n_cells, long long n_months, long long n_days, const int* month_start,
+                                    const double* monthly, double* daily);
+
 /* snowfall_prob (R/splash.point.R:560-578) */
 double splash_oracle_snowfall_prob(double tc, double lat, double elev);
 

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-SPLASH_ABI_VERSION = 3
+SPLASH_ABI_VERSION = 4
 SPLASH_NSTATE = 6
 
 SPLASH_OK, SPLASH_ERR_BAD_ARG, SPLASH_ERR_CUDA, SPLASH_ERR_NOMEM, SPLASH_ERR_NO_DEVICE = range(5)
@@ -101,6 +101,13 @@ class SplashUnswcOut(C.Structure):
     _fields_ = [
         ("cell_stride", C.c_int64), ("theta_i", C.c_void_p), ("wtd", C.c_void_p), ("w_z", C.c_void_p), ("se", C.c_void_p),
         ("mem_kind", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SplashM2dIn(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int64), ("n_months", C.c_int64), ("n_days", C.c_int64), ("in_stride", C.c_int64), ("out_stride", C.c_int64),
+        ("month_start", C.c_void_p), ("monthly", C.c_void_p), ("mem_kind", C.c_int32), ("out_f32", C.c_int32),
     ]
 
 

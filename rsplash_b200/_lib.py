@@ -14,6 +14,7 @@ from .build import LIB_PATH
 EXPORTS = (
     "splash_abi_version", "splash_ctx_create", "splash_ctx_destroy", "splash_last_error", "splash_count_months",
     "splash_grid_run", "splash_point_run", "splash_last_stats", "splash_debug_math", "splash_unswc_grid_run",
+    "splash_month2day_linear",
 )
 
 _lib = None
@@ -56,6 +57,8 @@ def load() -> C.CDLL:
     lib.splash_last_stats.restype = C.c_int
     lib.splash_unswc_grid_run.argtypes = [C.c_void_p, C.POINTER(_abi.SplashUnswcIn), C.POINTER(_abi.SplashUnswcOut)]
     lib.splash_unswc_grid_run.restype = C.c_int
+    lib.splash_month2day_linear.argtypes = [C.c_void_p, C.POINTER(_abi.SplashM2dIn), C.c_void_p]
+    lib.splash_month2day_linear.restype = C.c_int
     lib.splash_debug_math.argtypes = [C.c_void_p, C.c_int, C.c_int64, dp, dp]
     lib.splash_debug_math.restype = C.c_int
     if lib.splash_abi_version() != _abi.SPLASH_ABI_VERSION:

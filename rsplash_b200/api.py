@@ -7,7 +7,8 @@ return the same nine layers (R/splash.grid.R:449).  They only marshal numpy arra
 
 What stays outside (as in the survey's scope table): raster I/O, terrain derivation (slope,
 aspect, upslope area, latitude, resolution are *inputs* here, as they are for splash.point), and
-the random monthly->daily rain disaggregation.
+the random monthly->daily rain disaggregation (the deterministic interpolation of monthly temperature and
+radiation is `month2day_linear`).
 """
 from __future__ import annotations
 
@@ -161,3 +162,48 @@ def unSWC_grid(soil_data, uns_depth: float, wn, ctx: Context | None = None) -> d
     cout.theta_i, cout.wtd, cout.w_z, cout.se = _ptr(res["theta_i"]), _ptr(res["wtd"]), _ptr(res["w_z"]), _ptr(res["Se"])
     ctx.check(ctx.lib.splash_unswc_grid_run(ctx.handle, C.byref(cin), C.byref(cout)))
     return res
+
+
+def month_starts(time_index_month, time_index) -> np.ndarray:
+    """0-based position on the daily axis of each month's first day (time_index_month - time_index[1])."""
+    tm = np.asarray(time_index_month, dtype="datetime64[D]")
+    t0 = np.asarray(time_index, dtype="datetime64[D]")[0]
+    return ((tm - t0) / np.timedelta64(1, "D")).astype(np.int32)
+
+
+def month2day_linear(monthly, time_index_month, time_index, ctx: Context | None = None, dtype=np.float64,
+                     out_ptr: int | None = None, in_ptr: int | None = None, n_cells: int | None = None):
+    """approx(time_index_month, x, time_index, method = "linear", rule = 2)$y for every cell of a block: what
+    splash.point does to monthly tc and sw_in before anything else (R/splash.point.R:74-84).
+
+    monthly  [n_months, n_cells] (NaN = NA);  time_index_month  datetime64 month starts;  time_index  the daily axis.
+    Returns [n_days, n_cells] in `dtype` (float64, or float32 = the f32 forcing layout of splash_grid).
+    With in_ptr / out_ptr (device addresses of [n_months, n_cells] float64 and [n_days, n_cells] dtype arrays, e.g.
+    torch tensors' data_ptr()) the series are produced in HBM and nothing is returned.
+    """
+    ctx = ctx or default_context()
+    xs = np.ascontiguousarray(month_starts(time_index_month, time_index))
+    n_days = len(np.asarray(time_index))
+    f32 = np.dtype(dtype) == np.float32
+    if not f32 and np.dtype(dtype) != np.float64:
+        raise ValueError("dtype must be float64 or float32")
+    cin = _abi.SplashM2dIn()
+    cin.month_start = xs.ctypes.data_as(C.c_void_p)
+    cin.out_f32 = int(f32)
+    if (in_ptr is None) != (out_ptr is None):
+        raise ValueError("in_ptr and out_ptr go together")
+    if in_ptr is not None:
+        if n_cells is None:
+            raise ValueError("n_cells is required with device pointers")
+        cin.n_cells, cin.n_months, cin.n_days = int(n_cells), len(xs), n_days
+        cin.monthly, cin.mem_kind = C.c_void_p(int(in_ptr)), _abi.SPLASH_MEM_DEVICE
+        ctx.check(ctx.lib.splash_month2day_linear(ctx.handle, C.byref(cin), C.c_void_p(int(out_ptr))))
+        return None
+    monthly = np.ascontiguousarray(monthly, dtype=np.float64)
+    if monthly.ndim != 2 or monthly.shape[0] != len(xs):
+        raise ValueError("monthly must be [n_months, n_cells] with one row per element of time_index_month")
+    cin.n_cells, cin.n_months, cin.n_days = monthly.shape[1], monthly.shape[0], n_days
+    cin.monthly, cin.mem_kind = _ptr(monthly), _abi.SPLASH_MEM_HOST
+    out = np.empty((n_days, monthly.shape[1]), dtype=dtype)
+    ctx.check(ctx.lib.splash_month2day_linear(ctx.handle, C.byref(cin), _ptr(out)))
+    return out

@@ -963,6 +963,156 @@ __global__ void k_init_resume(Work w, double* cc, int64_t cpitch, double* diag, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Monthly -> daily forcing: stats::approx(time_index_month, x, time_index, method = "linear", rule = 2)$y as
+// splash.point applies it to monthly tc and sw_in (R/splash.point.R:74-84).  The knots are the non-NA months
+// (approx drops NA pairs), the interpolant is R's y[i] + (y[j] - y[i]) * ((v - x[i]) / (x[j] - x[i])), a day
+// that falls on a knot takes the knot's value, and days outside the knots hold the end values (rule = 2).  Fewer
+// than two non-NA months: the series is NA (:75-76).
+//   k_m2d_knots   per cell: first and last non-NA month (or -1 when fewer than two)
+//   k_month2day   one thread per cell and chunk of days; CTAs of one chunk are launched next to each other, so
+//                 the rows being written at any moment are few (the day-major layout puts consecutive days of a
+//                 cell n_cells elements apart)
+// HBM-bound: 8 (or 4) bytes written per cell-day, ~8 bytes read per cell-month.  The quotient is an integer
+// ratio a/b with 0 < a < b: for b <= 40000 the correctly rounded value is q0 + fma(-b, q0, a) * rb with
+// rb = 1/b rounded once per knot interval and q0 = a * rb (checked exhaustively, tools/m2d_divcheck.c), which
+// keeps the FP64 pipe below the store stream; longer gaps take the IEEE division.
+// ---------------------------------------------------------------------------------------------
+struct M2dParams {
+    const double* monthly;  // [n_months][ipitch]
+    int64_t ipitch;
+    void* out;              // [day - out_day0][opitch], double or float
+    int64_t opitch;
+    const int32_t* xs;      // [n_months] day index of each month's first day
+    int2* knots;            // [n_cells] first / last non-NA month
+    int64_t n_cells;
+    int n_months;
+    int64_t day0, day1;     // days this launch covers
+    int64_t out_day0;       // day held by row 0 of `out`
+    int64_t chunk;          // days per blockIdx.y
+};
+
+__global__ void __launch_bounds__(256) k_m2d_knots(M2dParams p) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_cells) return;
+    const double* y = p.monthly + c;
+    int n_ok = 0, first = -1, last = -1;
+    for (int m = 0; m < p.n_months; ++m) {
+        if (!isnan(__ldcs(y + (int64_t)m * p.ipitch))) {
+            ++n_ok;
+            if (first < 0) first = m;
+            last = m;
+        }
+    }
+    p.knots[c] = (n_ok < 2) ? make_int2(-1, -1) : make_int2(first, last);
+}
+
+template <typename OT, int V>
+struct M2dVec;
+template <> struct M2dVec<double, 1> { using T = double; };
+template <> struct M2dVec<double, 2> { using T = double2; };
+template <> struct M2dVec<float, 1> { using T = float; };
+template <> struct M2dVec<float, 2> { using T = float2; };
+template <> struct M2dVec<float, 4> { using T = float4; };
+
+// V adjacent cells per thread (one 8/16-byte store per day); kSync > 0 keeps the warps of a CTA within kSync
+// days of each other, so that a CTA writes whole 256*V-cell row segments close in time.
+template <typename OT, int V, int kSync>
+__global__ void __launch_bounds__(256) k_month2day(M2dParams p) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const bool active = c < p.n_cells;  // the host picks V so that n_cells % V == 0
+    if (kSync == 0 && !active) return;
+    const int64_t d0 = p.day0 + (int64_t)blockIdx.y * p.chunk;
+    const int64_t d1 = (d0 + p.chunk < p.day1) ? d0 + p.chunk : p.day1;
+    if (d0 >= d1) return;
+    struct Knot {
+        int j, last;
+        double x_lo, x_hi, y_lo, y_hi, xi, yi, xj, yj, b, rb, dy;
+    } k[V];
+    const double* y = p.monthly + c;
+    if (active) {
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int2 kn = p.knots[c + u];
+            const int first = kn.x, last = kn.y;
+            k[u].last = last;
+            if (first < 0) continue;
+            const double* yu = y + u;
+            k[u].x_lo = p.xs[first];
+            k[u].x_hi = p.xs[last];
+            k[u].y_lo = yu[(int64_t)first * p.ipitch];
+            k[u].y_hi = yu[(int64_t)last * p.ipitch];
+            // left knot of the chunk's first day: the last non-NA month that starts on or before d0
+            int i = first;
+            if ((double)d0 > k[u].x_lo) {
+                int lo = first, hi = last;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (p.xs[mid] <= d0) lo = mid; else hi = mid - 1;
+                }
+                i = lo;
+                while (isnan(yu[(int64_t)i * p.ipitch])) --i;  // stops at `first` at the latest
+            }
+            int j = i;
+            if (i < last) do ++j; while (isnan(yu[(int64_t)j * p.ipitch]));
+            k[u].j = j;
+            k[u].xi = p.xs[i];
+            k[u].yi = yu[(int64_t)i * p.ipitch];
+            k[u].xj = p.xs[j];
+            k[u].yj = yu[(int64_t)j * p.ipitch];
+            k[u].b = k[u].xj - k[u].xi;
+            k[u].rb = 1.0 / k[u].b;
+            k[u].dy = k[u].yj - k[u].yi;
+        }
+    }
+    OT* o = (OT*)p.out + c + (d0 - p.out_day0) * p.opitch;
+    for (int64_t d = d0; d < d1; ++d, o += p.opitch) {
+        if (active) {
+            const double v = (double)d;
+            OT r[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                Knot& q = k[u];
+                double w;
+                if (q.last < 0) {
+                    w = nan("");
+                } else if (v < q.x_lo) {
+                    w = q.y_lo;
+                } else if (v >= q.x_hi) {
+                    w = q.y_hi;
+                } else {
+                    while (v >= q.xj) {  // x[i] <= v < x[j], neighbouring knots (j <= last because v < x_hi)
+                        q.xi = q.xj;
+                        q.yi = q.yj;
+                        int j = q.j;
+                        do ++j; while (isnan(y[u + (int64_t)j * p.ipitch]));
+                        q.j = j;
+                        q.xj = p.xs[j];
+                        q.yj = y[u + (int64_t)j * p.ipitch];
+                        q.b = q.xj - q.xi;
+                        q.rb = 1.0 / q.b;
+                        q.dy = q.yj - q.yi;
+                    }
+                    const double a = v - q.xi;
+                    double t;
+                    if (q.b <= 40000.0) {
+                        const double t0 = a * q.rb;
+                        t = fma(fma(-q.b, t0, a), q.rb, t0);  // == a / b (see above)
+                    } else {
+                        t = a / q.b;
+                    }
+                    w = (v == q.xi) ? q.yi : q.yi + q.dy * t;
+                }
+                r[u] = (OT)w;
+            }
+            typename M2dVec<OT, V>::T pack;
+            memcpy(&pack, r, sizeof(pack));
+            __stcs((typename M2dVec<OT, V>::T*)o, pack);
+        }
+        if (kSync > 0 && ((d - d0) % kSync) == kSync - 1) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: day tables (SOLAR.cpp:98-124, 291-374) -- built with host libm like the reference does
 // ---------------------------------------------------------------------------------------------
 namespace hostsolar {
@@ -1373,6 +1523,119 @@ int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_uns
     if (d_out) cudaFree(d_out);
     if (rc != SPLASH_OK) return fail(ctx, rc, "splash_unswc_grid_run: %s", cudaGetErrorString(cudaGetLastError()));
     return SPLASH_OK;
+}
+
+int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* daily_out) {
+    if (!ctx) return SPLASH_ERR_BAD_ARG;
+    ctx->err.clear();
+    if (!in) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_month2day_linear: NULL in");
+    const int64_t nc = in->n_cells, nm = in->n_months, nd = in->n_days;
+    if (nc < 0 || nm < 0 || nd < 0 || nm > INT32_MAX) return fail(ctx, SPLASH_ERR_BAD_ARG, "negative or oversized n_cells/n_months/n_days");
+    const int64_t istride = in->in_stride ? in->in_stride : nc, ostride = in->out_stride ? in->out_stride : nc;
+    if (istride < nc || ostride < nc) return fail(ctx, SPLASH_ERR_BAD_ARG, "stride smaller than n_cells");
+    if (in->mem_kind != SPLASH_MEM_HOST && in->mem_kind != SPLASH_MEM_DEVICE)
+        return fail(ctx, SPLASH_ERR_BAD_ARG, "mem_kind must be SPLASH_MEM_HOST or SPLASH_MEM_DEVICE");
+    if (nc == 0 || nd == 0) return SPLASH_OK;
+    if (!daily_out || (nm > 0 && (!in->monthly || !in->month_start))) return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL monthly/month_start/daily_out");
+    for (int64_t m = 1; m < nm; ++m)
+        if (in->month_start[m] <= in->month_start[m - 1]) return fail(ctx, SPLASH_ERR_BAD_ARG, "month_start must be strictly increasing");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t S = ctx->s_run[0];
+    const size_t osz = in->out_f32 ? 4 : 8;
+    int32_t* d_xs = nullptr;
+    int2* d_knots = nullptr;
+    double* d_monthly = nullptr;
+    void* d_out = nullptr;
+    int rc = SPLASH_OK;
+    auto cu = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == SPLASH_OK) {
+            rc = (e == cudaErrorMemoryAllocation) ? SPLASH_ERR_NOMEM : SPLASH_ERR_CUDA;
+            fail(ctx, rc, "splash_month2day_linear: %s", cudaGetErrorString(e));
+        }
+        return e == cudaSuccess;
+    };
+    M2dParams p{};
+    p.ipitch = istride;
+    p.n_cells = nc;
+    p.n_months = (int)nm;
+    const int64_t day_chunk = getenv("SPLASH_M2D_CHUNK") ? std::max(1, atoi(getenv("SPLASH_M2D_CHUNK"))) : 512;
+    // launch shape (measured in profiles/README.md: one cell per thread, 512-day chunks, no lock-step is the most
+    // repeatable; the other shapes stay selectable for the round-2 study of the row-strided store stream)
+    const int want_v = getenv("SPLASH_M2D_VEC") ? atoi(getenv("SPLASH_M2D_VEC")) : 1;
+    const int sync_days = getenv("SPLASH_M2D_SYNC") ? atoi(getenv("SPLASH_M2D_SYNC")) : 0;
+    if (cu(cudaMalloc(&d_xs, (size_t)std::max<int64_t>(nm, 1) * 4)) && cu(cudaMalloc(&d_knots, (size_t)nc * sizeof(int2))) &&
+        (nm == 0 || cu(cudaMemcpyAsync(d_xs, in->month_start, (size_t)nm * 4, cudaMemcpyHostToDevice, S)))) {
+        p.xs = d_xs;
+        p.knots = d_knots;
+        bool have_knots = false;
+        auto launch = [&](int64_t day0, int64_t day1) {
+            if (!have_knots) {
+                k_m2d_knots<<<(unsigned)((nc + 255) / 256), 256, 0, S>>>(p);
+                have_knots = true;
+            }
+            // cells per thread: as many as one aligned 16-byte store holds, when the rows allow it
+            int V = 1;
+            for (int v = (int)(16 / osz); v > 1; v >>= 1)
+                if (v <= want_v && nc % v == 0 && (p.opitch * osz) % (v * osz) == 0 && ((uintptr_t)p.out % (v * osz)) == 0) {
+                    V = v;
+                    break;
+                }
+            const int64_t cta_x = (nc / V + 255) / 256;
+            p.chunk = day_chunk;
+            for (int64_t a = day0; a < day1 && rc == SPLASH_OK; a += p.chunk * 65535) {  // grid.y limit
+                p.day0 = a;
+                p.day1 = std::min(day1, a + p.chunk * 65535);
+                dim3 grid((unsigned)cta_x, (unsigned)((p.day1 - p.day0 + p.chunk - 1) / p.chunk));
+#define M2D_LAUNCH(OT, VV) \
+    do { \
+        if (sync_days > 0) k_month2day<OT, VV, 8><<<grid, 256, 0, S>>>(p); \
+        else k_month2day<OT, VV, 0><<<grid, 256, 0, S>>>(p); \
+    } while (0)
+                if (in->out_f32) {
+                    if (V == 4) M2D_LAUNCH(float, 4);
+                    else if (V == 2) M2D_LAUNCH(float, 2);
+                    else M2D_LAUNCH(float, 1);
+                } else {
+                    if (V == 2) M2D_LAUNCH(double, 2);
+                    else M2D_LAUNCH(double, 1);
+                }
+#undef M2D_LAUNCH
+            }
+            return cu(cudaGetLastError());
+        };
+        if (in->mem_kind == SPLASH_MEM_DEVICE) {
+            p.monthly = in->monthly;
+            p.out = daily_out;
+            p.opitch = ostride;
+            p.out_day0 = 0;
+            launch(0, nd);
+        } else {
+            // host arrays: the monthly block goes up once, the daily series come back in chunks of days
+            const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nd, ((int64_t)1 << 30) / std::max<int64_t>(1, nc * (int64_t)osz)));
+            if (cu(cudaMalloc(&d_monthly, (size_t)std::max<int64_t>(nm, 1) * nc * 8)) && cu(cudaMalloc(&d_out, (size_t)chunk * nc * osz)) &&
+                (nm == 0 || cu(cudaMemcpy2DAsync(d_monthly, (size_t)nc * 8, in->monthly, (size_t)istride * 8, (size_t)nc * 8, (size_t)nm,
+                                                 cudaMemcpyHostToDevice, S)))) {
+                p.monthly = d_monthly;
+                p.ipitch = nc;
+                p.out = d_out;
+                p.opitch = nc;
+                for (int64_t a = 0; a < nd && rc == SPLASH_OK; a += chunk) {
+                    const int64_t b = std::min(nd, a + chunk);
+                    p.out_day0 = a;
+                    if (!launch(a, b)) break;
+                    cu(cudaMemcpy2DAsync((char*)daily_out + (size_t)a * ostride * osz, (size_t)ostride * osz, d_out, (size_t)nc * osz,
+                                         (size_t)nc * osz, (size_t)(b - a), cudaMemcpyDeviceToHost, S));
+                    cu(cudaStreamSynchronize(S));
+                }
+            }
+        }
+    }
+    cu(cudaStreamSynchronize(S));
+    cudaFree(d_xs);
+    cudaFree(d_knots);
+    cudaFree(d_monthly);
+    cudaFree(d_out);
+    return rc;
 }
 
 

@@ -141,8 +141,35 @@ extern "C" SEXP splash_unswc_grid_R(SEXP soil, SEXP wn, SEXP uns_depth, SEXP dev
     return res;
 }
 
+// .Call("splash_month2day_linear_R", monthly, month_start, n_days, device)
+//   monthly : numeric matrix [cells x months] (raster::getValues of a monthly brick); month_start : integer vector,
+//   as.integer(time_index_month - time_index[1]); returns the [cells x days] matrix that
+//   approx(time_index_month, x, time_index, method = "linear", rule = 2)$y gives cell by cell
+//   (reference R/splash.point.R:74-84)
+extern "C" SEXP splash_month2day_linear_R(SEXP monthly, SEXP month_start, SEXP n_days, SEXP device) {
+    const R_xlen_t nm = XLENGTH(month_start);
+    const R_xlen_t nc = nm ? XLENGTH(monthly) / nm : 0;
+    const int nd = Rf_asInteger(n_days);
+    splash_m2d_in in = {0};
+    in.n_cells = nc;
+    in.n_months = nm;
+    in.n_days = nd;
+    in.month_start = INTEGER(month_start);
+    in.monthly = REAL(monthly);
+    in.mem_kind = SPLASH_MEM_HOST;
+    SEXP res = PROTECT(Rf_allocMatrix(REALSXP, (int)nc, nd));
+    splash_ctx* ctx = get_ctx(Rf_asInteger(device));
+    if (splash_month2day_linear(ctx, &in, REAL(res)) != SPLASH_OK) {
+        UNPROTECT(1);
+        Rf_error("libsplash_cuda: %s", splash_last_error(ctx));
+    }
+    UNPROTECT(1);
+    return res;
+}
+
 static const R_CallMethodDef call_methods[] = {{"splash_grid_run_R", (DL_FUNC)&splash_grid_run_R, 15},
                                                {"splash_unswc_grid_R", (DL_FUNC)&splash_unswc_grid_R, 4},
+                                               {"splash_month2day_linear_R", (DL_FUNC)&splash_month2day_linear_R, 4},
                                                {"splash_release_R", (DL_FUNC)&splash_release_R, 0},
                                                {NULL, NULL, 0}};
 

@@ -187,3 +187,16 @@ def unswc_cpu(soil, uns_depth, wn) -> dict:
     lib.splash_oracle_unswc_grid(n_cells, n_layers, p(soil), p(wn), float(uns_depth), p(out["theta_i"]), p(out["wtd"]),
                                  p(out["w_z"]), p(out["Se"]))
     return out
+
+
+def month2day_cpu(monthly, month_start, n_days) -> np.ndarray:
+    """stats::approx(..., method="linear", rule=2) per cell on the C restatement (R/splash.point.R:74-84)."""
+    lib = oracle()
+    monthly = np.ascontiguousarray(monthly, dtype=np.float64)
+    xs = np.ascontiguousarray(month_start, dtype=np.int32)
+    n_months, n_cells = monthly.shape
+    out = np.full((n_days, n_cells), np.nan)
+    lib.splash_oracle_month2day_linear.restype = None
+    lib.splash_oracle_month2day_linear.argtypes = [C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.splash_oracle_month2day_linear(n_cells, n_months, n_days, xs.ctypes.data, monthly.ctypes.data, out.ctypes.data)
+    return out
