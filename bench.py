@@ -517,6 +517,8 @@ def main():
                 "job_cell_days": job_total, "executed_cell_days": executed_total,
                 "spin_share_of_job": 1.0 - n_cells_total * (world if weak else 1) * nd / job_total,
                 "finite_fraction_wn": finite_frac,
+                # the series days alone over the same wall time, so that spin-up pass counts do not blur it
+                "nd_only_cell_days_per_s": n_cells_total * (world if weak else 1) * nd / (ms_per_step * 1e-3),
             },
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "stats_last_step": stats_steps[-1],
