@@ -1,7 +1,8 @@
 // rglue.cpp -- .Call entry points that bind libsplash_cuda into the rsplash R package.
 //
-// NOT BUILT HERE: this image has no R (no R.h / Rinternals.h); the file is what a maintainer adds
-// under rsplash/src/ (see INTEGRATION.md).  It uses only the plain R C API (no Rcpp), keeps no
+// This image has no R (no R.h / Rinternals.h): the file is what a maintainer adds under rsplash/src/ (see
+// INTEGRATION.md); here it is compiled against the R C-API stand-in of tests/r_stub and driven from pytest
+// (tests/test_rglue_cpu.py, tests/test_rglue_gpu.py).  It uses only the plain R C API (no Rcpp), keeps no
 // pointers after return, and turns every non-zero status into an R error.
 //
 // Replaces, per block of cells, the body of clFun (reference R/splash.grid.R:277-308): the
