@@ -1112,6 +1112,78 @@ __global__ void __launch_bounds__(256) k_month2day(M2dParams p) {
     }
 }
 
+// Row-band form of the same interpolation.  The month that holds a day, and the quotient (v - x_i)/(x_j - x_i)
+// when both of its neighbouring months are present, depend on the day only: the host tabulates them (IEEE
+// division, as R does it).  A CTA then sweeps a band of D day-rows over K*256 adjacent cells, row by row: a
+// cell-day is two cached monthly values, one multiply-add pair and one store, and a warp's consecutive stores
+// stay inside one row.  Cells with NA months next to the day take the general search below (knots from
+// k_m2d_knots), which follows approx1() as the walk kernel does.
+struct M2dBand {
+    const double* monthly;
+    int64_t ipitch;
+    void* out;
+    int64_t opitch;
+    const int32_t* xs;
+    const int2* knots;
+    const int32_t* day_m;  // [n_days] month that holds the day (largest m with xs[m] <= d), -1 before the first month
+    const double* day_q;   // [n_days] (d - xs[m]) / (xs[m+1] - xs[m]); 0 on a month's first day and in the last month
+    int64_t n_cells;
+    int n_months;
+    int64_t day0, day1, out_day0;
+    int D;
+};
+
+__device__ __noinline__ double m2d_general(const double* y, int64_t ipitch, const int32_t* xs, int2 kn, int m, int64_t d) {
+    if (kn.x < 0) return nan("");  // fewer than two non-NA months, R/splash.point.R:75-76
+    const double v = (double)d;
+    const double x_lo = xs[kn.x], x_hi = xs[kn.y];
+    if (v < x_lo) return y[(int64_t)kn.x * ipitch];   // rule = 2
+    if (v >= x_hi) return y[(int64_t)kn.y * ipitch];
+    int i = m, j = m + 1;                              // kn.x <= m < kn.y here
+    while (isnan(y[(int64_t)i * ipitch])) --i;         // stops at kn.x at the latest
+    while (isnan(y[(int64_t)j * ipitch])) ++j;         // stops at kn.y at the latest
+    const double xi = xs[i], xj = xs[j], yi = y[(int64_t)i * ipitch], yj = y[(int64_t)j * ipitch];
+    if (v == xi) return yi;
+    return yi + (yj - yi) * ((v - xi) / (xj - xi));
+}
+
+template <typename OT, int K>
+__global__ void __launch_bounds__(256) k_month2day_band(M2dBand p) {
+    const int64_t cbase = (int64_t)blockIdx.x * (256 * K) + threadIdx.x;
+    const int64_t d0 = p.day0 + (int64_t)blockIdx.y * p.D;
+    const int64_t d1 = (d0 + p.D < p.day1) ? d0 + p.D : p.day1;
+    int cur_m = INT_MIN;
+    double yi[K], yj[K];
+    OT* o = (OT*)p.out + (d0 - p.out_day0) * p.opitch + cbase;
+    for (int64_t d = d0; d < d1; ++d, o += p.opitch) {
+        const int m = __ldg(p.day_m + d);
+        const double q = __ldg(p.day_q + d);
+        if (m != cur_m) {
+            cur_m = m;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int64_t c = cbase + k * 256;
+                yi[k] = yj[k] = nan("");
+                if (c < p.n_cells && m >= 0) {
+                    yi[k] = p.monthly[(int64_t)m * p.ipitch + c];
+                    yj[k] = (m + 1 < p.n_months) ? p.monthly[(int64_t)(m + 1) * p.ipitch + c] : yi[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int64_t c = cbase + k * 256;
+            if (c >= p.n_cells) continue;
+            double r;
+            if (!isnan(yi[k]) && !isnan(yj[k]))
+                r = (q == 0.0) ? yi[k] : yi[k] + (yj[k] - yi[k]) * q;
+            else
+                r = m2d_general(p.monthly + c, p.ipitch, p.xs, p.knots[c], m, d);
+            __stcs(o + k * 256, (OT)r);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: day tables (SOLAR.cpp:98-124, 291-374) -- built with host libm like the reference does
 // ---------------------------------------------------------------------------------------------
@@ -1546,6 +1618,8 @@ int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* dail
     int2* d_knots = nullptr;
     double* d_monthly = nullptr;
     void* d_out = nullptr;
+    int32_t* d_day_m = nullptr;
+    double* d_day_q = nullptr;
     int rc = SPLASH_OK;
     auto cu = [&](cudaError_t e) {
         if (e != cudaSuccess && rc == SPLASH_OK) {
@@ -1568,11 +1642,53 @@ int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* dail
         p.xs = d_xs;
         p.knots = d_knots;
         bool have_knots = false;
+        const char* kern = getenv("SPLASH_M2D_KERNEL");
+        const bool band = kern && !strcmp(kern, "band");
+        const int band_d = getenv("SPLASH_M2D_BAND_D") ? std::max(1, atoi(getenv("SPLASH_M2D_BAND_D"))) : 16;
+        const int band_k = getenv("SPLASH_M2D_BAND_K") ? atoi(getenv("SPLASH_M2D_BAND_K")) : 4;
+        auto launch_band = [&](int64_t day0, int64_t day1) {
+            if (!d_day_m) {  // per-day table: month index and quotient, host arithmetic (IEEE division like R)
+                std::vector<int32_t> dm((size_t)nd);
+                std::vector<double> dq((size_t)nd);
+                int64_t m = -1;
+                for (int64_t d = 0; d < nd; ++d) {
+                    while (m + 1 < nm && in->month_start[m + 1] <= d) ++m;
+                    dm[(size_t)d] = (int32_t)m;
+                    dq[(size_t)d] = (m >= 0 && m + 1 < nm)
+                                        ? (double)(d - in->month_start[m]) / (double)(in->month_start[m + 1] - in->month_start[m]) : 0.0;
+                }
+                if (!cu(cudaMalloc(&d_day_m, (size_t)nd * 4)) || !cu(cudaMalloc(&d_day_q, (size_t)nd * 8)) ||
+                    !cu(cudaMemcpy(d_day_m, dm.data(), (size_t)nd * 4, cudaMemcpyHostToDevice)) ||
+                    !cu(cudaMemcpy(d_day_q, dq.data(), (size_t)nd * 8, cudaMemcpyHostToDevice)))
+                    return false;
+            }
+            M2dBand b{};
+            b.monthly = p.monthly; b.ipitch = p.ipitch; b.out = p.out; b.opitch = p.opitch; b.xs = p.xs; b.knots = p.knots;
+            b.day_m = d_day_m; b.day_q = d_day_q; b.n_cells = nc; b.n_months = (int)nm; b.out_day0 = p.out_day0; b.D = band_d;
+            const int K = (band_k >= 4) ? 4 : (band_k >= 2 ? 2 : 1);
+            const int64_t cta_x = (nc + 256 * K - 1) / (256 * K);
+            for (int64_t a = day0; a < day1 && rc == SPLASH_OK; a += (int64_t)band_d * 65535) {
+                b.day0 = a;
+                b.day1 = std::min(day1, a + (int64_t)band_d * 65535);
+                dim3 grid((unsigned)cta_x, (unsigned)((b.day1 - b.day0 + band_d - 1) / band_d));
+#define M2D_BAND(OT) \
+    do { \
+        if (K == 4) k_month2day_band<OT, 4><<<grid, 256, 0, S>>>(b); \
+        else if (K == 2) k_month2day_band<OT, 2><<<grid, 256, 0, S>>>(b); \
+        else k_month2day_band<OT, 1><<<grid, 256, 0, S>>>(b); \
+    } while (0)
+                if (in->out_f32) M2D_BAND(float);
+                else M2D_BAND(double);
+#undef M2D_BAND
+            }
+            return cu(cudaGetLastError());
+        };
         auto launch = [&](int64_t day0, int64_t day1) {
             if (!have_knots) {
                 k_m2d_knots<<<(unsigned)((nc + 255) / 256), 256, 0, S>>>(p);
                 have_knots = true;
             }
+            if (band) return launch_band(day0, day1);
             // cells per thread: as many as one aligned 16-byte store holds, when the rows allow it
             int V = 1;
             for (int v = (int)(16 / osz); v > 1; v >>= 1)
@@ -1635,6 +1751,8 @@ int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* dail
     cudaFree(d_knots);
     cudaFree(d_monthly);
     cudaFree(d_out);
+    cudaFree(d_day_m);
+    cudaFree(d_day_q);
     return rc;
 }
 

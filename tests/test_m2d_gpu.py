@@ -38,6 +38,30 @@ def test_launch_shapes_give_the_same_bits(ctx, monkeypatch, vec, sync, chunk):
         assert np.array_equal(api.month2day_linear(m, months, days, ctx=ctx, dtype=np.float32), ref.astype(np.float32), equal_nan=True)
 
 
+@pytest.mark.parametrize("band_d,band_k", [(16, 4), (1, 1), (7, 2), (64, 4), (5000, 1)])
+def test_row_band_kernel_gives_the_same_bits(ctx, monkeypatch, band_d, band_k):
+    """the row-band form (per-day month index and quotient tabulated on the host) against the same restatement"""
+    monkeypatch.setenv("SPLASH_M2D_KERNEL", "band")
+    monkeypatch.setenv("SPLASH_M2D_BAND_D", str(band_d))
+    monkeypatch.setenv("SPLASH_M2D_BAND_K", str(band_k))
+    for n_cells, seed in ((1028, 6), (37, 9), (1, 10)):
+        m, months, days = make_case(n_cells=n_cells, n_years=3, seed=seed)
+        ref = ol.month2day_cpu(m, api.month_starts(months, days), len(days))
+        assert np.array_equal(api.month2day_linear(m, months, days, ctx=ctx), ref, equal_nan=True)
+        with np.errstate(over="ignore"):
+            assert np.array_equal(api.month2day_linear(m, months, days, ctx=ctx, dtype=np.float32), ref.astype(np.float32), equal_nan=True)
+    # a daily axis that starts before the first month and ends long after the last one
+    m, months, days = make_case(n_cells=64, n_years=2, seed=11)
+    xs = api.month_starts(months, days)
+    cin = _abi.SplashM2dIn()
+    shifted = np.ascontiguousarray(xs + 10, dtype=np.int32)
+    out = np.empty((len(days) + 50, 64))
+    cin.n_cells, cin.n_months, cin.n_days = 64, len(xs), out.shape[0]
+    cin.month_start, cin.monthly, cin.mem_kind = shifted.ctypes.data, m.ctypes.data, _abi.SPLASH_MEM_HOST
+    ctx.check(ctx.lib.splash_month2day_linear(ctx.handle, C.byref(cin), C.c_void_p(out.ctypes.data)))
+    assert np.array_equal(out, ol.month2day_cpu(m, shifted, out.shape[0]), equal_nan=True)
+
+
 def test_strides_and_bad_arguments(ctx):
     m, months, days = make_case(n_cells=50, n_years=2, seed=4)
     xs = np.ascontiguousarray(api.month_starts(months, days))

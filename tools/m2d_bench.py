@@ -19,7 +19,9 @@ months, days = axes(2001, n_years)
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1)
 src = torch.randn((len(months), n_cells), dtype=torch.float64, device=dev, generator=g) * 10
-src[torch.rand(src.shape, device=dev, generator=g) < 0.02] = float("nan")
+nan_frac = float(os.environ.get("M2D_NAN_FRAC", "0.02"))  # months set to NA at random (every warp then meets gaps)
+if nan_frac > 0:
+    src[torch.rand(src.shape, device=dev, generator=g) < nan_frac] = float("nan")
 dst = torch.empty((len(days), n_cells), dtype=torch.float32 if f32 else torch.float64, device=dev)
 ctx = Context(0)
 run = lambda: api.month2day_linear(None, months, days, ctx=ctx, dtype=np.float32 if f32 else np.float64, in_ptr=src.data_ptr(),
@@ -44,6 +46,16 @@ def measure():
     return float(np.median(ts))
 
 
+if len(sys.argv) > 4 and sys.argv[4] == "band":  # row-band kernel sweep (development)
+    os.environ.pop("SPLASH_M2D_KERNEL", None)
+    print(f"{'f32' if f32 else 'f64'} walk (default): {measure():.2f} ms")
+    os.environ["SPLASH_M2D_KERNEL"] = "band"
+    for k in ((1, 4) if os.environ.get("M2D_QUICK") else (1, 2, 4)):
+        for d in ((16, 64) if os.environ.get("M2D_QUICK") else (4, 8, 16, 32, 64, 256)):
+            os.environ.update(SPLASH_M2D_BAND_D=str(d), SPLASH_M2D_BAND_K=str(k))
+            ms = measure()
+            print(f"{'f32' if f32 else 'f64'} band K {k} D {d}: {ms:.2f} ms  {bytes_alg / ms / 1e6:.0f} GB/s  {bytes_alg / ms / 1e6 / peak:.3f}")
+    sys.exit(0)
 if len(sys.argv) > 4 and sys.argv[4] == "sweep":  # launch-shape sweep (development)
     for vec in ((1, 2, 4) if f32 else (1, 2)):
         for sync in (0, 8):
