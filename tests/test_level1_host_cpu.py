@@ -1,0 +1,69 @@
+"""CPU: the DEVICE day step (rsplash_b200/csrc/splash_model.cuh + splash_math.cuh: level-1 arithmetic, own
+exp/log/acos/sin, FP32 viscosity) compiled for the host (tests/host_emul/) against the C restatement of the
+reference.  Same gates and the same conditioning screen as the GPU parity tests, so the arithmetic the kernels
+execute is checked on every machine, GPU or not.  The scheduling side of the kernels is what the `-m gpu` tests add."""
+import numpy as np
+import pytest
+
+from rsplash_b200 import _abi
+from tests import conditioning, parity
+from tests import host_emul_harness as he
+from tests import oracle_lib as ol
+from tests.fixtures import GOLDEN_DIR, load_golden, load_problem
+from tests.synthetic import make_problem
+
+
+def _gates(got, ref, cells):
+    sub = lambda r: {**{k: np.asarray(r[k])[:, cells] for k in _abi.OUTPUT_NAMES}, "cell_diag": np.asarray(r["cell_diag"])[:, cells]}
+    parity.compare(sub(got), sub(ref))
+    parity.compare_diag(sub(got)["cell_diag"], sub(ref)["cell_diag"])
+
+
+@pytest.mark.parametrize("level", [1, 0])
+def test_host_build_of_the_day_step_meets_the_gates_on_well_conditioned_cells(level):
+    prob, dates = make_problem(n_cells=600, n_years=1, seed=41)
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    got = he.run(prob, level=level)
+    for k in _abi.OUTPUT_NAMES:  # NaN masks: every cell
+        assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
+    for name in ("Tt", "snow_days", "snowfall_days", "depth"):
+        i = _abi.DIAG_NAMES.index(name)
+        assert np.array_equal(got["cell_diag"][i], ref["cell_diag"][i], equal_nan=True), name
+    stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
+    cells = np.flatnonzero(stable)
+    assert len(cells) >= 0.4 * prob.n_cells
+    _gates(got, ref, cells)
+
+
+@pytest.mark.parametrize("name", ["bourne", "atneu"])
+def test_host_build_reproduces_the_reference_goldens(name):
+    """Real-data cases (outputs of the compiled reference, tests/golden/): no ill-conditioned day in them, so the
+    device arithmetic has to meet the full gates on every day."""
+    prob, dates = load_problem(name)
+    got = he.run(prob)
+    gold = load_golden(name)
+    parity.compare(got, gold, prefix="daily_")
+    parity.compare_diag(got["cell_diag"], gold["cell_diag"])
+
+
+def test_host_build_reproduces_the_sacru_grid_golden():
+    """22 101 cells of the package's CRU example (tests/golden/sacru_*): daily layers of the probe cells, all diagnostics."""
+    prob, dates = load_problem("sacru")
+    gold = load_golden("sacru")
+    probe = np.load(GOLDEN_DIR + "/sacru_probe.npz")["probe"]
+    got = he.run(prob)
+    parity.compare({k: got[k][:, probe] for k in _abi.OUTPUT_NAMES}, gold, prefix="daily_")
+    parity.compare_diag(got["cell_diag"], gold["cell_diag"])
+
+
+def test_tiny_lambda_on_dry_soil_host_build():
+    """The reference's bp/u overflow in moist_surf through the device arithmetic, without a GPU."""
+    prob, dates = make_problem(n_cells=400, n_years=1, seed=5)
+    rng = np.random.default_rng(1)
+    for row, (lo, hi) in enumerate([(5, 20), (38, 46), (1, 3), (20, 40), (1.45, 1.7)]):
+        prob.soil[row] = rng.uniform(lo, hi, prob.n_cells).astype(np.float32)
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    got = he.run(prob)
+    stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
+    assert stable.sum() >= 0.4 * prob.n_cells
+    _gates(got, ref, np.flatnonzero(stable))
