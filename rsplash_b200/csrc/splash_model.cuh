@@ -384,18 +384,34 @@ __device__ __forceinline__ Transm column_transmittance_core(const CC& cc, double
     const double a = cc(C_ILAM) * M::log(x);  // log shared by x^(1/lambda) and (x^(1/lambda))^(3 lambda + 1)
     const double psi_m = SPLASH_FDIV(bub, M::exp(a));
     double wtd = SPLASH_DIV_1000(bub - psi_m);
+    bool clamped = false;
     if (wtd < 0.0 || isnan(wtd)) {
         wtd = 0.01;
+        clamped = true;
     } else if (wtd > depth) {
         wtd = depth;
+        clamped = true;
     }
     r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
     const double r1 = M::exp(e3 * a);  // (bub/psi_m)^e3 with bub/psi_m == x^(1/lambda)
-    // second power: its base is 1 up to rounding noise unless wtd was clamped; first-order expansion there
-    const double q = SPLASH_FDIV(bub, psi_m + (wtd * 1000.0));
-    const double qm1 = q - 1.0;
-    const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : M::exp(e3 * M::log(q));
-    double t_uns = (ksat_visc * bub / e3) * (r1 - r2);
+    const double den = psi_m + (wtd * 1000.0);
+    double dr;  // (bub/psi_m)^e3 - (bub/den)^e3
+    if (!clamped) {
+        // the second base is 1 up to rounding noise (den == bub): first-order expansion
+        const double q = SPLASH_FDIV(bub, den);
+        const double qm1 = q - 1.0;
+        const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : M::exp(e3 * M::log(q));
+        dr = r1 - r2;
+    } else {
+        // wtd was clamped: on dry soil both bases are x^(1/lambda)-small and differ by depth/psi_m ~ 1e-15 relative.
+        // Two separately composed powers (|e3 ln b| ulp each) lose that difference -- and whether the drainage Q
+        // below is tiny or exactly 0 decides between a finite and an infinite t_drain (:1470).  The ratio form
+        // r1 * ((den_ratio)^e3 - 1) keeps it, as the reference's two pow() of nearly equal bases do.
+        const double t = e3 * M::log(SPLASH_FDIV(psi_m, den));
+        const double em1 = (fabs(t) < 1e-5) ? t * (1.0 + 0.5 * t) : M::exp(t) - 1.0;
+        dr = -(r1 * em1);
+    }
+    double t_uns = (ksat_visc * bub / e3) * dr;
 #else
     const double theta_i = (sm) / cc(C_D1000);
     const double psi_m = bub / pow((((theta_i - cc(C_THR)) / cc(C_DTH))), cc(C_ILAM));

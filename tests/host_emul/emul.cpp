@@ -93,7 +93,16 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
         double AI = nan(""), w1 = 0.0;
         DayOut o;
         double rain, snowfall, f_sw, f_tc, f_pn;
-        for (int it = 0; it < 2 * kSpinYear; ++it) {
+        int passes = 1;
+        const bool resume = opts && opts->skip_spinup && opts->state_init;
+        if (resume) {  // k_init_resume: the carried state and aridity index instead of the spin-up
+            const double* s0 = opts->state_init + c;
+            st = CellState{s0[0 * nc], s0[1 * nc], s0[2 * nc], s0[3 * nc], s0[4 * nc]};
+            AI = s0[5 * nc];
+            lateral_consts(cc, AI);
+            passes = 0;
+        }
+        for (int it = 0; !resume && it < 2 * kSpinYear; ++it) {
             const int d = (it < kSpinYear) ? it : it - kSpinYear;
             spin_forcing(d, f_sw, f_tc, f_pn);
             splash_day(cc, spin[d], mt, f_sw, f_tc, f_pn, st, o, rain, snowfall);
@@ -111,8 +120,7 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
             }
         }
         // ---- k_spin_check / k_spin_rest ----
-        int passes = 1;
-        for (;;) {
+        while (!resume) {
             const CellState Ek = st;
             CellState chk = Ek;
             spin_forcing(0, f_sw, f_tc, f_pn);

@@ -40,10 +40,15 @@ def lib(level: int = 1):
     return _libs[level]
 
 
-def run(problem: ol.GridProblem, level: int = 1) -> dict:
+def run(problem: ol.GridProblem, level: int = 1, state_init=None) -> dict:
     """The block through the host build of the device day step: daily outputs, state_final, cell_diag."""
+    import numpy as np
+
     cout, arrays = ol.alloc_out(problem.n_days, problem.n_cells)
     opts = _abi.SplashOpts()
+    if state_init is not None:
+        st = np.ascontiguousarray(state_init, dtype=np.float64)
+        opts.skip_spinup, opts.state_init = 1, st.ctypes.data
     cin = problem.c_in()
     rc = lib(level).splash_emul_grid_run(C.byref(cin), C.byref(opts), C.byref(cout))
     if rc != 0:

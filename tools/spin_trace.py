@@ -1,6 +1,8 @@
 """Development aid: replay one cell's spin-up pass by pass through the resume entry, on the GPU and on the C
 restatement from the SAME start state each pass, and report the first day of each pass where they part ways.
-Usage: spin_trace.py n_cells n_years seed cell [cell ...]   (one-year problems: the series is the spin-up year)"""
+Usage: spin_trace.py n_cells n_years seed cell [cell ...]   (one-year problems: the series is the spin-up year)
+SPIN_TRACE_HOST=1 replays through the host build of the device day step (tests/host_emul) instead of the GPU."""
+import os
 import sys
 
 import numpy as np
@@ -17,6 +19,10 @@ KEYS = ("wn", "snow", "ro", "aet", "pet", "cond", "bflow", "netr", "sm_lim")
 
 
 def gpu(p, st):
+    if os.environ.get("SPIN_TRACE_HOST"):
+        from tests import host_emul_harness as he
+
+        return he.run(p, state_init=st)
     return api.splash_grid(p.sw_in, p.tc, p.pn, p.lat, p.elev, p.slop, p.asp, p.soil, p.au, p.resolution, dates,
                            monthly_out=False, return_diag=True, return_state=True, **({} if st is None else {"state_init": st}))
 
