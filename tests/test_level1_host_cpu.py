@@ -67,3 +67,34 @@ def test_tiny_lambda_on_dry_soil_host_build():
     stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
     assert stable.sum() >= 0.4 * prob.n_cells
     _gates(got, ref, np.flatnonzero(stable))
+
+
+def _check_all(prob):
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    got = he.run(prob)
+    for k in _abi.OUTPUT_NAMES:
+        assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
+    stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
+    assert stable.sum() >= 0.4 * prob.n_cells
+    _gates(got, ref, np.flatnonzero(stable))
+    return got, ref
+
+
+def test_missing_values_short_series_and_scalar_au_host_build():
+    """The NA semantics of the device day step (SURVEY B-7), a series shorter than the spin-up year
+    (R/splash.point.R:141-144) and the length(Au) == 1 layout (:106-110), as tests/test_edge_gpu.py runs them."""
+    prob, dates = make_problem(n_cells=96, n_years=1, seed=4)
+    prob.tc[:, 0:8] = np.nan
+    prob.pn[:, 8:16] = np.nan
+    prob.soil[:, 16:24] = np.nan
+    prob.sw_in[100:110, 24:32] = np.nan
+    prob.elev[32:40] = np.nan
+    got, ref = _check_all(prob)
+    assert np.isnan(got["wn"][:, 0:24]).all() and np.isfinite(got["pet"][:, 16:24]).all()
+    prob, dates = make_problem(n_cells=64, n_years=1, seed=3)
+    nd = 200
+    short = ol.GridProblem(prob.year[:nd], prob.doy[:nd], prob.month[:nd], prob.sw_in[:nd], prob.tc[:nd], prob.pn[:nd], prob.lat,
+                           prob.elev, prob.slop, prob.asp, prob.resolution, prob.soil, prob.au)
+    _check_all(short)
+    prob, dates = make_problem(n_cells=64, n_years=1, seed=6, au_layers=1)
+    _check_all(prob)
