@@ -4,6 +4,8 @@
  *   pp_pow_explog  x^y evaluated as exp(y*log(x)) (the error a composed power has: |y ln x| ulp)
  *   pp_exp/pp_log  exp()/log() with 1 call in 8 moved by +-1 ulp
  *   pp_sin/pp_acos sin()/acos() with 1 call in 8 moved by +-1 ulp
+ *   pp_var         a marked intermediate (PP_VAR in splash_oracle.c) with 1 evaluation in 8 moved by +-1 ulp: what any
+ *                  other implementation of the transcendentals upstream of it does to it
  * Constant exponents that GCC folds in the reference build (x^2, 1/x, sqrt, x^3) are left alone. */
 #include <math.h>
 #include <stdint.h>
@@ -40,3 +42,4 @@ double pp_exp(double x) { uint64_t a; memcpy(&a, &x, 8); return bump(exp(x), mix
 double pp_log(double x) { uint64_t a; memcpy(&a, &x, 8); return bump(log(x), mix(a + 2)); }
 double pp_sin(double x) { uint64_t a; memcpy(&a, &x, 8); return bump(sin(x), mix(a + 3)); }
 double pp_acos(double x) { uint64_t a; memcpy(&a, &x, 8); return bump(acos(x), mix(a + 4)); }
+double pp_var(double x) { uint64_t a; memcpy(&a, &x, 8); return bump(x, mix(a + 5)); }

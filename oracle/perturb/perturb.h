@@ -8,10 +8,15 @@ double pp_exp(double);
 double pp_log(double);
 double pp_sin(double);
 double pp_acos(double);
-#ifdef PERTURB_ALL   /* every libm call of the path at once */
+double pp_var(double);
+#ifdef PERTURB_ALL   /* every libm call of the path at once, and the marked variables */
 #define PERTURB_POW
 #define PERTURB_EXPLOG
 #define PERTURB_TRIG
+#define PERTURB_VARS
+#endif
+#ifdef PERTURB_VARS  /* PP_VAR(x) in splash_oracle.c: net radiation, econ, water density, Ksat_visc moved by an ulp */
+#define PP_VAR(x) pp_var(x)
 #endif
 #ifdef PERTURB_POW
 #define pow pp_pow

@@ -12,8 +12,13 @@
  */
 #define _GNU_SOURCE
 #include "splash_oracle.h"
+/* PP_VAR marks the intermediates that the perturbed builds of oracle/perturb move by an ulp (identity here) */
+#ifndef PP_VAR
+#define PP_VAR(x) (x)
+#endif
 
 #include <math.h>
+#include <stdio.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -408,7 +413,7 @@ static void evap_daily(double lat, double elv, double sw, int n, int y, double s
                        double asp, double snow, double nd, etr_t* out) {
     srad_t sr;
     solar_daily(lat, elv, n, y, sw_in, tc, slop, asp, snow, nd, sw, &sr);
-    double ru = sr.ru, rv = sr.rv, rw = sr.rw, rnl = sr.rnl, hn = sr.hn, rn_d = sr.rn_d, rnn_d = sr.rnn_d;
+    double ru = sr.ru, rv = sr.rv, rw = sr.rw, rnl = sr.rnl, hn = sr.hn, rn_d = PP_VAR(sr.rn_d), rnn_d = sr.rnn_d;
 
     double tw = 0.0; /* :100-105 */
     if (tc < 0.0) {
@@ -420,9 +425,9 @@ static void evap_daily(double lat, double elv, double sw, int n, int y, double s
     double patm = elv2pres(elv);
     double s = sat_slope(tc);
     double lv = enthalpy_vap(tc);
-    double pw = density_h2o(tc, patm);
+    double pw = PP_VAR(density_h2o(tc, patm));
     double g = psychro(tc, patm);
-    double econ = s / (lv * pw * (s + g));
+    double econ = PP_VAR(s / (lv * pw * (s + g)));
     double visc = calc_viscosity_h2o(tw, patm); /* :120 (double->float args, float->double result) */
     /* 3. condensation, :124 */
     double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
@@ -542,6 +547,14 @@ typedef struct {
     double sm, ro, swe, bflow, sqout, tdr, nd, pet;
 } smr_t;
 
+/* Optional trace of every day step (single-threaded runs of one cell): tools/day_trace_host.py diffs it against the
+ * same trace of the device day step built for the host. */
+static FILE* g_trace = NULL;
+void splash_oracle_set_trace(const char* path) {
+    if (g_trace) fclose(g_trace);
+    g_trace = (path && path[0]) ? fopen(path, "w") : NULL;
+}
+
 /* SPLASH::run_one_day == SPLASH::quick_run (live code only), src/SPLASH.cpp:920-1588 / :150-918.
  * dvap_out receives the EVAP values run_all reads afterwards (:1904-1907). */
 static void run_one_day(double lat, double elv, int n, int y, double wn, double sw_in, double tc, double pn,
@@ -603,7 +616,7 @@ static void run_one_day(double lat, double elv, int n, int y, double wn, double 
 
     /* 05. water balance, :1260-1284 */
     double int_perm = Ksat / kfluidity;
-    double Ksat_visc = int_perm * ((pw * kG) / visc) * 3.6;
+    double Ksat_visc = PP_VAR(int_perm * ((pw * kG) / visc) * 3.6);
     double inflow = pn + dvap.cond + snowmelt;
     double surf_moist = splash_oracle_moist_surf(depth, 10.0, bub_press, wn, SAT, RES, lambda);
     double theta_m = cxx_max(Wmax / (depth * 1000.0), theta_i);
@@ -771,6 +784,9 @@ static void run_one_day(double lat, double elv, int n, int y, double wn, double 
     dsoil->nd = nd;
     dsoil->pet = dvap.pet; /* quick_run only, :916 */
     if (dvap_out) *dvap_out = dvap;
+    if (g_trace) /* development aid: one line per day step, in call order (splash_oracle_set_trace) */
+        fprintf(g_trace, "n=%d wn=%.17g snow=%.17g qin=%.17g td=%.17g nd=%.17g ro=%.17g pet=%.17g aet=%.17g cond=%.17g bflow=%.17g netr=%.17g\n",
+                n, sm, snow, qin_nday, tdrain_out, nd, ro, dvap.pet, dvap.aet, dvap.cond, T, dvap.rn_d / 1e6);
 }
 
 /* SPLASH::spin_up, src/SPLASH.cpp:1594-1749 */

@@ -80,6 +80,10 @@ void splash_oracle_unswc_grid(long long n_cells, long long n_layers, const doubl
 void splash_oracle_month2day_linear(long long n_cells, long long n_months, long long n_days, const int* month_start,
                                     const double* monthly, double* daily);
 
+/* Development aid: write one line per day step (state after the day and its fluxes, in the order SPLASH::spin_up and
+ * run_all call run_one_day) to `path`; NULL or "" stops.  Use with one cell and n_threads = 1. */
+void splash_oracle_set_trace(const char* path);
+
 /* snowfall_prob (R/splash.point.R:560-578) */
 double splash_oracle_snowfall_prob(double tc, double lat, double elev);
 

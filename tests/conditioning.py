@@ -13,6 +13,9 @@ libraries (oracle/perturb/, built by `make -C oracle sens`):
     POWEXPLOG  pow(x, y) evaluated as exp(y*log(x))
     EXPLOG     1 exp()/log() in 8 returns the neighbouring double
     TRIG       1 sin()/acos() in 8 returns the neighbouring double
+    VARS       net radiation, econ, water density and Ksat_visc of 1 day in 8 moved to the neighbouring double (what a
+               different but equally good exp/sin/acos upstream does to them): flips the exact ties of the snow
+               energy balance (inflow == aet to the bit, hence R == 0, on days without melt and without daylight)
     FMA        the same source compiled with -mfma -ffp-contract=fast (an `-march=native` R build)
     RECIP      the same source compiled with -freciprocal-math (x/y as x*(1/y): divisions move by an ulp)
     ALL1/ALL2  two dense draws of everything at once: every other pow/exp/log/sin/acos call moved, with
@@ -36,7 +39,7 @@ from rsplash_b200 import _abi
 from tests import oracle_lib as ol
 
 SENS_DIR = os.path.join(ol.ORACLE_DIR, "_sens")
-SPARSE = ("POW", "POWEXPLOG", "EXPLOG", "TRIG", "FMA", "RECIP")  # one kind of operation at a time, 1 call in 8
+SPARSE = ("POW", "POWEXPLOG", "EXPLOG", "TRIG", "VARS", "FMA", "RECIP")  # one kind of operation at a time, 1 call in 8
 DENSE = ("ALL1", "ALL2")                                        # everything at once, every other call
 VARIANTS = SPARSE + DENSE
 

@@ -6,6 +6,7 @@
 // (tiles, rounds, pool, cycle skipping) is not reproduced: it moves no arithmetic.
 #include <cuda_runtime.h>  // the shim of this directory
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -36,6 +37,16 @@ double ld(const void* base, int64_t i) { return (double)((const FT*)base)[i]; }
 
 extern "C" int splash_emul_level(void) { return SPLASH_LEVEL; }
 
+// SPLASH_EMUL_TRACE=<file>: one line per day step in the order SPLASH::spin_up / run_all call run_one_day (the
+// first spin_up's own equilibrium loop included, and each check day repeated as day 1 of the pass it starts), so
+// that the stream can be diffed against a trace of the restatement.  Development aid; single cell.
+static FILE* g_trace = nullptr;
+static void trace(int n, const CellState& st, const DayOut& o) {
+    if (g_trace)
+        fprintf(g_trace, "n=%d wn=%.17g snow=%.17g qin=%.17g td=%.17g nd=%.17g ro=%.17g pet=%.17g aet=%.17g cond=%.17g bflow=%.17g netr=%.17g\n",
+                n, st.wn, st.snow, st.qin, st.td, st.nd, o.ro, o.pet, o.aet, o.cond, o.bflow, o.netr);
+}
+
 extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts* opts, splash_grid_out* out) {
     if (!in || !out) return SPLASH_ERR_BAD_ARG;
     const int64_t nc = in->n_cells, nd = in->n_days;
@@ -50,6 +61,7 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
     build_day_tables(in->year, in->doy, in->month, nd, kSpinYear, tab, spin);
     const MonthTab mt = build_month_table();
     double* outs[9] = {out->wn, out->ro, out->pet, out->aet, out->snow, out->cond, out->bflow, out->netr, out->sm_lim};
+    g_trace = (getenv("SPLASH_EMUL_TRACE") && nc == 1) ? fopen(getenv("SPLASH_EMUL_TRACE"), "w") : nullptr;
     auto forcing = [&](const void* a, int64_t d, int64_t c) { return f32 ? ld<float>(a, d * istride + c) : ld<double>(a, d * istride + c); };
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t c = 0; c < nc; ++c) {
@@ -106,17 +118,41 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
             const int d = (it < kSpinYear) ? it : it - kSpinYear;
             spin_forcing(d, f_sw, f_tc, f_pn);
             splash_day(cc, spin[d], mt, f_sw, f_tc, f_pn, st, o, rain, snowfall);
+            trace(d + 1, st, o);
+            if (it == kSpinYear) w1 = st.wn;
             if (it < kSpinYear) {
                 if (!isnan(o.pet)) sum_pet.add(o.pet);
                 const double P = rain + snowfall;
                 if (!isnan(P)) sum_p.add(P);
+                if (it == 0) w1 = st.wn;
                 if (it == kSpinYear - 1) {
+                    if (g_trace) {  // the first spin_up's equilibrium loop: dead work in the reference, traced only
+                        CellState e = st;
+                        double w = w1;
+                        for (int k = 1;; ++k) {
+                            CellState chk = e;
+                            DayOut oo;
+                            double r2, s2;
+                            spin_forcing(0, f_sw, f_tc, f_pn);
+                            splash_day(cc, spin[0], mt, f_sw, f_tc, f_pn, chk, oo, r2, s2);
+                            trace(1, chk, oo);
+                            double diff = chk.wn - w;
+                            if (diff < 0) diff = w - chk.wn;
+                            if (!((diff > tol) && (k < max_spin))) break;
+                            trace(1, chk, oo);
+                            e = chk;
+                            w = e.wn;
+                            for (int dd = 1; dd < kSpinYear; ++dd) {
+                                spin_forcing(dd, f_sw, f_tc, f_pn);
+                                splash_day(cc, spin[dd], mt, f_sw, f_tc, f_pn, e, oo, r2, s2);
+                                trace(dd + 1, e, oo);
+                            }
+                        }
+                    }
                     AI = sum_pet.value() / sum_p.value();
                     lateral_consts(cc, AI);
                     st = CellState{RES, 0.0, 0.0, 0.0, 0.0};
                 }
-            } else if (it == kSpinYear) {
-                w1 = st.wn;
             }
         }
         // ---- k_spin_check / k_spin_rest ----
@@ -125,14 +161,17 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
             CellState chk = Ek;
             spin_forcing(0, f_sw, f_tc, f_pn);
             splash_day(cc, spin[0], mt, f_sw, f_tc, f_pn, chk, o, rain, snowfall);
+            trace(1, chk, o);
             double diff = chk.wn - w1;
             if (diff < 0) diff = w1 - chk.wn;
             if (!((diff > tol) && (passes < max_spin))) { st = Ek; break; }  // the day-365 state is handed over
+            trace(1, chk, o);
             st = chk;
             w1 = st.wn;
             for (int d = 1; d < kSpinYear; ++d) {
                 spin_forcing(d, f_sw, f_tc, f_pn);
                 splash_day(cc, spin[d], mt, f_sw, f_tc, f_pn, st, o, rain, snowfall);
+                trace(d + 1, st, o);
             }
             ++passes;
         }
@@ -141,6 +180,7 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
         for (int64_t d = 0; d < nd; ++d) {
             f_sw = forcing(in->sw_in, d, c); f_tc = forcing(in->tc, d, c); f_pn = forcing(in->pn, d, c);
             splash_day(cc, tab[d], mt, f_sw, f_tc, f_pn, st, o, rain, snowfall);
+            trace(in->doy[d], st, o);
             if (snowfall > 0.0) ++n_snowfall;
             double sm_lim = (st.wn - RES) / cc(C_WRR);
             if (sm_lim < 0) sm_lim = 0.0;
@@ -158,5 +198,7 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
             diag[SPLASH_DIAG_SPIN_PASSES * nc] = (double)passes; diag[SPLASH_DIAG_SNOWFALL_DAYS * nc] = (double)n_snowfall;
         }
     }
+    if (g_trace) fclose(g_trace);
+    g_trace = nullptr;
     return SPLASH_OK;
 }
