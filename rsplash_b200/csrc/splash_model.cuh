@@ -809,7 +809,11 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         // the reference forms bp/u first (:1945), which overflows to -inf once |bp|/u > DBL_MAX (dry soil with a
         // tiny lambda: u = x^(1/lambda) ~ 1e-306); head/bp is then +inf and theta_BC collapses onto theta_r
         if (inv_u > fabs(cc(C_TEN_BP)) * 1.7976931348623157e307) head = INFINITY;
-        double theta_BC = cc(C_DTH) * M::exp(cc(C_NLAM) * M::log(head)) + theta_r;
+        double hp = M::exp(cc(C_NLAM) * M::log(head));
+        // an air-entry pressure of exactly 0 (pedotransfer result of some sandy, gravelly soils) makes the base -inf:
+        // pow(-inf, y) is +0 for y < 0, +inf for y > 0 and 1 for y == 0 (C11 F.10.4.4), not NaN
+        if (head == -INFINITY) hp = (cc(C_NLAM) < 0.0) ? 0.0 : ((cc(C_NLAM) > 0.0) ? INFINITY : ((cc(C_NLAM) == 0.0) ? 1.0 : hp));
+        double theta_BC = cc(C_DTH) * hp + theta_r;
 #else
         const double bp = cc(C_BP10);
         const double water_pot_BC = bp / pow((((theta_mean - theta_r) / cc(C_DTH))), cc(C_ILAM));

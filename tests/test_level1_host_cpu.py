@@ -98,3 +98,20 @@ def test_missing_values_short_series_and_scalar_au_host_build():
     _check_all(short)
     prob, dates = make_problem(n_cells=64, n_years=1, seed=6, au_layers=1)
     _check_all(prob)
+
+
+def test_zero_air_entry_pressure_host_build():
+    """Sandy, gravelly, organic soils for which the pedotransfer functions return an air-entry pressure of exactly 0
+    (bub_press == -0): moist_surf then raises -inf to the power -lambda, which is +0 in C (not NaN), and on a day
+    with intense inflow the reference's Green-Ampt step yields NaN from there on (cell 4405 of this draw, found by
+    tools/parity_scan_host.py).  NaN masks must match for every cell."""
+    big, dates = make_problem(n_cells=5000, n_years=1, seed=503, lat_range=(-25.0, 25.0))
+    prob = big.subset(np.arange(4300, 4500))
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    c = 4405 - 4300
+    assert ref["cell_diag"][_abi.DIAG_NAMES.index("bub_press"), c] == 0 and np.isnan(ref["wn"][:, c]).any()
+    got = he.run(prob)
+    for k in _abi.OUTPUT_NAMES:
+        assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
+    stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
+    _gates(got, ref, np.flatnonzero(stable))
