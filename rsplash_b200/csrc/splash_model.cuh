@@ -787,6 +787,17 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     aet_d += rx * rw * rv * (sin_hn - sin_hi);
     aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
     aet_d *= (24.0 / kPI);
+#if SPLASH_L1_RECIP
+    // Days without melt and without an evaporation integral (polar night): sublimation = (AE*econ)*1000 is negative
+    // (deposition) and aet becomes ((sublimation/1000)/econ * econ) * 1000 -- the same operations run backwards and
+    // forwards again, which return sublimation exactly for 99.8 % of the values, so that aet == inflow and
+    // R = infi - aet (SPLASH.cpp:1283) is exactly 0.  `R > 0` would switch the same-day upslope input on (:1468,
+    // a jump of Qt/Ai ~ 1e-3 mm); with reciprocal multiplications the round trip is off by an ulp on 22 % of the
+    // days.  Take the round trip's fixed point.
+    if (aet_d == 0.0 && snowmelt_tot == 0.0)
+        aet_d = 0.0 - sublimation;
+    else
+#endif
     aet_d -= (melt_enrg * econ * 1000.0);
     if (aet_d < 0.0) {
         aet_d = 0.0;
