@@ -2,7 +2,7 @@
 (tests/host_emul) against the C restatement on many synthetic draws; reports the cells that are well-conditioned in
 the reference (stable under every perturbed-libm variant) and still leave the gates -- candidates for places where
 the level-1 arithmetic has to reproduce a floating-point accident of the reference.
-usage: parity_scan_host.py n_cells n_years seed [seed ...]     (LAT_RANGE="50,72" restricts the latitudes)"""
+usage: parity_scan_host.py n_cells n_years seed [seed ...]     (LAT_RANGE="50,72" restricts the latitudes, AU_LAYERS=1: scalar Au)"""
 import os
 import sys
 
@@ -18,6 +18,8 @@ from tests.synthetic import make_problem  # noqa: E402
 n_cells, n_years = int(sys.argv[1]), int(sys.argv[2])
 for seed in map(int, sys.argv[3:]):
     kw = {"lat_range": tuple(float(v) for v in os.environ["LAT_RANGE"].split(","))} if os.environ.get("LAT_RANGE") else {}
+    if os.environ.get("AU_LAYERS"):
+        kw["au_layers"] = int(os.environ["AU_LAYERS"])
     prob, dates = make_problem(n_cells, n_years, seed=seed, **kw)
     ref = ol.run_cpu(prob, monthly=False, core="oracle")
     got = he.run(prob)
