@@ -1,0 +1,44 @@
+"""GPU: the cells that taught level-1 arithmetic its five lessons -- tiny lambda on dry soil,
+Kb on gentle slopes, the dry-soil transmittance difference, zero air-entry pressure, the polar-night sublimation
+round trip -- and their neighbours, through the kernels and through the host build of the same headers
+(tests/host_emul): same NaN masks, same spin-up pass counts, states within 1e-9 mm.  (The host build is what the CPU
+suite holds against the reference; this test ties the kernels to it.)"""
+import numpy as np
+import pytest
+
+from rsplash_b200 import _abi, api
+from tests import host_emul_harness as he
+from tests import oracle_lib as ol
+from tests.synthetic import make_problem
+
+pytestmark = pytest.mark.gpu
+
+CASES = ((5000, 503, {"lat_range": (-25.0, 25.0)}, slice(4380, 4430)),   # cell 4405: bub_press == -0
+         (4000, 601, {"lat_range": (60.0, 80.0)}, slice(1210, 1260)),    # cell 1237: polar-night round trip
+         (4000, 601, {"lat_range": (60.0, 80.0)}, slice(1700, 1740)),    # cell 1720: the same
+         (5000, 204, {}, slice(3500, 3540)),                             # cell 3521: dry-soil transmittance difference
+         (5000, 101, {}, slice(2270, 2300)))                             # cell 2284: tiny lambda on dry soil
+
+
+def test_kernels_and_host_build_agree_on_the_special_cells(ctx):
+    parts, dates = [], None
+    for n, seed, kw, sl in CASES:
+        prob, dates = make_problem(n, 1, seed=seed, **kw)
+        parts.append(prob.subset(np.arange(n)[sl]))
+    p0 = parts[0]
+    cat = lambda f, axis: np.concatenate([getattr(p, f) for p in parts], axis=axis)
+    prob = ol.GridProblem(p0.year, p0.doy, p0.month, cat("sw_in", 1), cat("tc", 1), cat("pn", 1), cat("lat", 0), cat("elev", 0),
+                          cat("slop", 0), cat("asp", 0), cat("resolution", 0), cat("soil", 1), cat("au", 1))
+    host = he.run(prob)
+    got = api.splash_grid(prob.sw_in, prob.tc, prob.pn, prob.lat, prob.elev, prob.slop, prob.asp, prob.soil, prob.au,
+                          prob.resolution, dates, monthly_out=False, ctx=ctx, return_diag=True)
+    ip = _abi.DIAG_NAMES.index("spin_passes")
+    assert np.array_equal(got["cell_diag"][ip], host["cell_diag"][ip])
+    for k in _abi.OUTPUT_NAMES:
+        assert np.array_equal(np.isnan(got[k]), np.isnan(host[k])), k
+    for k in ("wn", "snow", "ro", "bflow"):
+        d = np.abs(got[k] - host[k])
+        assert np.nanmax(d) <= 1e-9, (k, float(np.nanmax(d)))
+    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    assert np.array_equal(np.isnan(got["wn"]), np.isnan(ref["wn"]))
+    assert (np.nanmax(np.abs(got["wn"] - ref["wn"]), axis=0) > 1e-6).sum() <= 2   # measured: 1 (ill-conditioned in the reference)
