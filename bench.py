@@ -3,24 +3,25 @@
 
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
     synthetic 5-arcmin global grid, 2 332 800 land cells x 10 years daily (3652 days) incl. spin-up,
-    monthly outputs (splash.grid's default sim.control).
+    monthly outputs (splash.grid's default sim.control).  The grid is counter-based
+    (rsplash_b200/synthetic.py: Grid; every value a function of seed, global cell, day, field), so every
+    rank's shard, every row block and the CPU baseline's sample are subsets of the same grid.
 Multi-GPU (cells are independent: no data-path collective, only the max-time / sum-job-size all-reduce):
-    --scaling weak (default)  every rank integrates one such grid with its own forcing realisation (an
-                              ensemble member), so the per-GPU work is fixed as N grows;
-    --scaling strong          ONE grid sharded by rows over the ranks (contiguous row ranges with ~equal
-                              cell counts).  Its speed-up is capped by the reference algorithm itself: a
-                              cell that never converges spins for 1000 sequential year passes, a chain of
-                              3.6e5 dependent day steps (~2.5 s) that no amount of sharding shortens
-                              (DESIGN.md, section 4).
-
+    --scaling strong (default)  ONE grid; blocks of 8 grid rows are dealt round-robin to the ranks, as the
+                                reference's scheduler deals row blocks to its workers
+                                (R/splash.grid.R:264-268, 312-314).  `config.weak_value` reports, beside it,
+                                the throughput with one whole grid per rank.
+    --scaling weak              every rank integrates one whole grid (its own forcing realisation).
 A step is one whole-job pass of the hot path over the rank's shard:
     value  inputs resident in HBM (forcing stored as f32 -- lossless, the rasters are FLT4S -- all
            arithmetic f64), outputs written to HBM; timed around splash_grid_run(DEVICE pointers)
-    e2e    the same job through the C ABI with HOST buffers (pinned, f64 like R's REAL()): the shard
-           is fed block of rows by block of rows as the reference's clFun scheduler does
-           (R/splash.grid.R:264-268), host->device and device->host copies inside the timed region
-The numerator is the job size as the reference defines it: n_cells * n_days plus the spin-up
-cell-days its algorithm requires (365 for the aridity pass + passes * 366 per cell).
+    e2e    the same job through the C ABI with HOST buffers (pinned, f64 like R's REAL()): the shard is fed
+           block of rows by block of rows through the block scheduler (splash_cluster_submit / _wait, the
+           reference's sendCall / recvOneData, R/splash.grid.R:312-314, 359-400), host->device and
+           device->host copies inside the timed region.  At most 3 timed passes (`e2e.steps`).
+The numerator is the job size as the reference defines it: n_cells * n_days plus the spin-up cell-days its
+algorithm requires (365 for the aridity pass + passes * 366 per cell); `config.executed_*` quote the
+cell-days the GPU actually simulated (exact cycle skipping removes work).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C] [--years Y]
 N > 1 is launched by torchrun (one rank per GPU, NCCL); RANK/LOCAL_RANK/WORLD_SIZE come from the env.
@@ -46,7 +47,10 @@ from rsplash_b200 import _abi, synthetic  # noqa: E402
 METRIC = "splash.grid cell-days/sec"
 UNIT = "cell-days/s"
 FIRST_YEAR = 2001
-
+GRID_SEED = 20240
+ROW_BLOCK = 8        # grid rows per scheduling block of the strong-scaling shards
+E2E_MAX_STEPS = 3    # timed passes of the host-fed leg (each moves ~220 GB over PCIe at N = 1)
+ROOFLINE_MAX_STEPS = 3
 
 
 def fp64_work_per_cell_day():
@@ -59,7 +63,7 @@ def fp64_work_per_cell_day():
     return 0.0, 0.0, "no ncu count committed"
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -68,11 +72,29 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=synthetic.N_CELLS_5ARCMIN)
     ap.add_argument("--years", type=int, default=10)
     ap.add_argument("--e2e-blocks", type=int, default=0, help="row blocks per rank for the e2e leg (0 = auto)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="cells of the CPU baseline sample")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="calls in flight per GPU in the e2e leg")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="cells of the CPU baseline / parity sample")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling figure at N > 1")
+    return ap.parse_args(argv)
+
+
+def plan_seconds(args, world: int) -> dict:
+    """Rough wall-clock plan of one bench.py run (seconds), so that a CPU test can hold it under the driver's per-N limit.
+    Rates measured in round 2 on the pool's B200 boxes (profiles/README.md): resident pass 2.6 s at N = 1, host-fed pass 4.5 s."""
+    frac = (args.cells / synthetic.N_CELLS_5ARCMIN) * (args.years / 10.0)
+    pass_s = max(0.9, 2.8 * frac / (world if args.scaling == "strong" else 1))   # chain-bound below ~0.9 s
+    e2e_s = max(1.2, 5.0 * frac / (world if args.scaling == "strong" else 1))
+    p = {"startup": 75.0, "generate": 6.0 * frac + 4.0,
+         "value": (args.warmup + args.steps) * pass_s,
+         "roofline": (2 + min(args.steps, ROOFLINE_MAX_STEPS)) * pass_s,
+         "e2e": 0.0 if args.no_e2e else 70.0 * frac + (1 + min(args.steps, E2E_MAX_STEPS)) * e2e_s + 8.0 * frac,
+         "weak": 0.0 if (world == 1 or args.no_weak or args.scaling == "weak") else 6.0 * frac + 3 * 2.8 * frac,
+         "cpu": 0.0 if (world > 1 or args.no_cpu) else 25.0 * (args.cpu_sample / 4096.0) * (args.years / 10.0) + 10.0}
+    p["total"] = sum(p.values())
+    return p
 
 
 def peaks():
@@ -141,43 +163,35 @@ class ClockSampler:
 
 def required_spin_days(passes) -> int:
     """Spin-up cell-days of the reference algorithm: aridity pass + passes x (365 + check day)."""
-    return int((365 + passes.to("cpu").double() * 366).sum().item()) if hasattr(passes, "to") else int(
-        (365 + np.asarray(passes, dtype=np.float64) * 366).sum())
+    p = passes.to("cpu").double().numpy() if hasattr(passes, "to") else np.asarray(passes, dtype=np.float64)
+    return int((365 + p * 366).sum())
 
 
 # --------------------------------------------------------------------------------------------------
-# workload
+# workload: which cells a rank owns
 # --------------------------------------------------------------------------------------------------
-def cell_range(world, rank, n_cells):
-    rows = synthetic.land_cells_per_row(n_cells)
-    return synthetic.shard_rows(rows, world)[rank], rows
+def rank_cells(grid: synthetic.Grid, world: int, rank: int, strong: bool):
+    """-> list of (c0, c1) contiguous global cell ranges of this rank, ascending.  Strong scaling: blocks of
+    ROW_BLOCK grid rows dealt round-robin (block b -> rank b % world); weak: the whole grid."""
+    if not strong or world == 1:
+        return [(0, grid.n_cells)]
+    rs = grid.row_start
+    n_rows = len(grid.rows_n)
+    segs = []
+    for b, r0 in enumerate(range(0, n_rows, ROW_BLOCK)):
+        if b % world != rank:
+            continue
+        c0, c1 = int(rs[r0]), int(rs[min(n_rows, r0 + ROW_BLOCK)])
+        if c1 > c0:
+            if segs and segs[-1][1] == c0:
+                segs[-1] = (segs[-1][0], c1)
+            else:
+                segs.append((c0, c1))
+    return segs
 
 
-def build_cells(torch, device, n_cells, c0, c1, seed=1234):
-    """Per-cell attributes of the global grid (same for every world size), sliced to [c0, c1)."""
-    rows = synthetic.land_cells_per_row(n_cells)
-    lat_rows = synthetic.row_latitudes()
-    lat_all = np.repeat(lat_rows, rows)
-    xp = synthetic.backend(seed, device)
-    lat = xp.f32(xp.asarray(lat_all))
-    cells = synthetic.make_cells(xp, lat, flat_fraction=0.5)
-    sl = slice(c0, c1)
-    out = {k: cells[k][sl].contiguous() for k in ("lat", "elev", "slop", "asp", "resolution")}
-    out["soil"] = torch.stack([a[sl] for a in cells["soil"]]).contiguous()
-    out["au"] = torch.stack([a[sl] for a in cells["au"]]).contiguous()
-    return out
-
-
-def fill_forcing(torch, device, cells, doy, seed, out_sw, out_tc, out_pn, chunk_days=32):
-    """Generate the forcing of `cells` into preallocated [n_days, n] tensors, a few days at a time."""
-    xp = synthetic.backend(seed, device)
-    doy_t = torch.as_tensor(doy.astype(np.float64), device=device)
-    for d0 in range(0, len(doy), chunk_days):
-        d1 = min(len(doy), d0 + chunk_days)
-        sw, tc, pn = synthetic.make_forcing(xp, cells["lat"], cells["elev"], doy_t[d0:d1])
-        out_sw[d0:d1].copy_(sw)
-        out_tc[d0:d1].copy_(tc)
-        out_pn[d0:d1].copy_(pn)
+def seg_index(segs) -> np.ndarray:
+    return np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in segs]) if segs else np.zeros(0, np.int64)
 
 
 def grid_in_struct(n_cells, n_days, year, doy, month, sw, tc, pn, cells, mem_kind, f32):
@@ -207,21 +221,24 @@ def grid_out_struct(n_out, n_cells, ptrs, diag, mem_kind):
 # --------------------------------------------------------------------------------------------------
 # reference / CPU arm
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_problem(sample_cells, n_years, seed=99):
-    """A bounded sample of the same workload generator for the CPU legs (numpy backend)."""
+def sample_indices(n_cells: int, sample_cells: int) -> np.ndarray:
+    """Global cell indices of the CPU sample: evenly spread over the grid (every latitude band)."""
+    return np.unique(np.linspace(0, n_cells - 1, min(sample_cells, n_cells)).astype(np.int64))
+
+
+def cpu_sample_problem(sample_cells, n_years, n_cells=synthetic.N_CELLS_5ARCMIN):
+    """The CPU legs' bounded sample: a SUBSET of the benchmark grid (same seed, same generator)."""
     from tests import oracle_lib as ol
 
-    rows = synthetic.land_cells_per_row(synthetic.N_CELLS_5ARCMIN)
-    lat_all = np.repeat(synthetic.row_latitudes(), rows)
-    pick = np.linspace(0, len(lat_all) - 1, sample_cells).astype(np.int64)  # every latitude band
-    xp = synthetic.backend(seed)
-    lat = xp.f32(lat_all[pick])
-    cells = synthetic.make_cells(xp, lat, flat_fraction=0.5)
+    grid = synthetic.Grid(n_cells, GRID_SEED)
+    pick = sample_indices(n_cells, sample_cells)
+    cells = grid.cells(pick)
     dates = synthetic.daily_dates(FIRST_YEAR, n_years)
     year, doy, month = _abi.time_axes(dates)
-    sw, tc, pn = synthetic.make_forcing(xp, lat, cells["elev"], doy.astype(np.float64))
-    return ol.GridProblem(year, doy, month, sw, tc, pn, lat, cells["elev"], cells["slop"], cells["asp"],
-                          cells["resolution"], np.stack(cells["soil"]), np.stack(cells["au"]))
+    sw, tc, pn = grid.forcing(cells, doy)
+    prob = ol.GridProblem(year, doy, month, sw, tc, pn, cells["lat"], cells["elev"], cells["slop"], cells["asp"],
+                          cells["resolution"], cells["soil"], cells["au"])
+    return prob, pick
 
 
 def time_cpu(prob, core, threads):
@@ -233,40 +250,44 @@ def time_cpu(prob, core, threads):
     return dt, r
 
 
-def cpu_leg(sample_cells, n_years, steps=1, warmup=0):
+def cpu_leg(sample_cells, n_years, steps=1, warmup=0, n_cells=synthetic.N_CELLS_5ARCMIN):
     """Times the reference's own CPU implementation (unmodified C++ core from oracle/_ref when it
-    was compiled, else the C restatement) on all host cores.  Returns (value, info dict)."""
+    was compiled, else the C restatement) on all host cores.  Returns (value, seconds, info, problem, pick, result)."""
     from tests import oracle_lib as ol
 
     ol.oracle()
     kind = "reference" if ol.have_ref() else "port"
     core = "ref" if kind == "reference" else "oracle"
     threads = os.cpu_count() or 1
-    prob = cpu_sample_problem(sample_cells, n_years)
+    prob, pick = cpu_sample_problem(sample_cells, n_years, n_cells)
     # pass counts (hence the job size) from the restated core: it is bit-identical to the reference core
     _, r0 = time_cpu(prob, "oracle", threads)
     job = prob.n_cells * prob.n_days + required_spin_days(r0["cell_diag"][_abi.DIAG_NAMES.index("spin_passes")])
     for _ in range(warmup):
         time_cpu(prob, core, threads)
-    times = [time_cpu(prob, core, threads)[0] for _ in range(max(1, steps))]
+    times, res = [], None
+    for _ in range(max(1, steps)):
+        dt, res = time_cpu(prob, core, threads)
+        times.append(dt)
     dt = float(np.mean(times))
+    res["cell_diag"][_abi.DIAG_NAMES.index("spin_passes")] = r0["cell_diag"][_abi.DIAG_NAMES.index("spin_passes")]
     info = {"value": job / dt, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"{prob.n_cells} cells x {prob.n_days} days (+ spin-up) of the same synthetic grid, "
-                      f"C++ core only ({'unmodified reference sources' if kind == 'reference' else 'C restatement'}; "
+            "sample": f"{prob.n_cells} cells x {prob.n_days} days (+ spin-up), a subset of the benchmark grid (same counter-based "
+                      f"generator and seed), C++ core only ({'unmodified reference sources' if kind == 'reference' else 'C restatement'}; "
                       f"R-side prep restated in C), {threads} threads, {dt:.2f} s per pass"}
-    return job / dt, dt, info
+    return job / dt, dt, info, prob, pick, res
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    value, dt, info = cpu_leg(args.cpu_sample, args.years, steps=args.steps, warmup=args.warmup)
+    value, dt, info, _, _, _ = cpu_leg(args.cpu_sample, args.years, steps=args.steps, warmup=args.warmup, n_cells=args.cells)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic 5-arcmin global grid x {args.years} years daily incl. spin-up, monthly outputs; "
-                               f"CPU sample of {args.cpu_sample} cells", "cells": args.cpu_sample, "days_per_cell": None},
+                               f"CPU sample of {args.cpu_sample} cells of that grid", "cells": args.cpu_sample, "days_per_cell": None},
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,9 +295,78 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def parity_block(prob, ref, got_layers, got_passes) -> dict:
+    """GPU results of the sample cells (monthly layers, [n_out, n]) against the reference run of the same cells:
+    NaN masks, the north_star gates on monthly values, and -- for the cells outside them -- whether the reference
+    itself is ill-conditioned there (tests/conditioning.py: its own result moves under a 1-ulp libm change)."""
+    from tests import parity
+
+    n = prob.n_cells
+    mask_equal = True
+    off = np.zeros(n, dtype=bool)
+    worst = {}
+    for k in _abi.OUTPUT_NAMES:
+        g, r = got_layers[k], ref[k]
+        gm, rm = np.isnan(g), np.isnan(r)
+        if not np.array_equal(gm, rm):
+            mask_equal = False
+            off |= (gm != rm).any(0)
+        ok = ~gm & ~rm & np.isfinite(g) & np.isfinite(r)
+        d = np.where(ok, np.abs(g - r), 0.0)
+        if k in parity.FLUX:
+            lim = parity.REL_FLUX * np.abs(np.where(ok, r, 0.0)) + parity.ABS_GUARD * 31
+            bad = d > lim
+            w = float((d / np.maximum(np.abs(np.where(ok, r, 1.0)), 1e-3)).max()) if ok.any() else 0.0
+        else:
+            lim = 1e-8 if k == "sm_lim" else parity.ABS_STATE_MM * (31 if k in ("ro", "bflow") else 1)
+            bad = d > lim
+            w = float(d.max()) if ok.any() else 0.0
+        off |= bad.any(0)
+        worst[k] = w
+    passes_equal = int((got_passes == ref["cell_diag"][_abi.DIAG_NAMES.index("spin_passes")]).sum())
+    out = {"cells_compared": int(n), "layers": "9 monthly layers", "nan_masks_equal": bool(mask_equal),
+           "cells_outside_gates": int(off.sum()), "spin_passes_equal_cells": passes_equal, "worst_error": worst,
+           "gates": "<= 1e-9 relative on pet/netr/aet/cond, <= 1e-6 mm on wn/snow (x31 on monthly sums ro/bflow), 1e-8 on sm_lim",
+           "against": "oracle/_ref (unmodified reference C++ core) run in this process on the same cells"}
+    if off.any():
+        try:
+            from tests import conditioning
+            sub = prob.subset(np.flatnonzero(off))
+            sparse, _ = conditioning.stable_cells(sub, None, conditioning.SPARSE)
+            dense, _ = conditioning.stable_cells(sub, None, conditioning.DENSE)
+            out["outside_of_which_reference_stable_sparse"] = int(sparse.sum())
+            out["outside_of_which_reference_stable_dense"] = int((sparse & dense).sum())
+        except Exception as e:  # the screen needs the perturbed oracle builds (make -C oracle sens)
+            out["conditioning_screen"] = f"unavailable: {e}"
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------------------
+class Shard:
+    """A rank's cells of one grid, resident on the device: per-cell attributes (f64) and f32 forcing."""
+
+    def __init__(self, torch, device, grid, segs, doy, filler=None):
+        self.segs = segs
+        self.index = seg_index(segs)
+        self.nc = len(self.index)
+        nd = len(doy)
+        self.cells_np = grid.cells(self.index)
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+        self.cells = {k: dev(self.cells_np[k]) for k in ("lat", "elev", "slop", "asp", "resolution", "soil", "au")}
+        self.filler = filler or synthetic.DeviceFiller(grid, doy, device)
+        self.f = [torch.empty((nd, self.nc), dtype=torch.float32, device=device) for _ in range(3)]
+        o = 0
+        for a, b in segs:  # the generator fills contiguous cell ranges
+            sub = {k: (v[..., o:o + (b - a)] if isinstance(v, np.ndarray) else v) for k, v in self.cells_np.items()}
+            self.filler.fill(sub, self.f[0][:, o:], self.f[1][:, o:], self.f[2][:, o:])
+            o += b - a
+
+    def ptrs(self):
+        return {k: v.data_ptr() for k, v in self.cells.items()}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -290,44 +380,28 @@ def main():
     import torch.distributed as dist
 
     from rsplash_b200 import build
-    from rsplash_b200._lib import Context
+    from rsplash_b200._lib import Cluster, Context
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libsplash_cuda has no CPU path (use --impl reference for the CPU arm)")
+    t_start = time.perf_counter()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     build.build()
+    if not os.path.exists(os.path.join(ROOT, "tools", "synth", "libsplash_synth.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tools", "synth")], check=True, capture_output=True)
     ctx = Context(local_rank)
 
-    n_cells_total = args.cells
-    weak = args.scaling == "weak"
-    if weak:  # one whole grid per rank
-        (c0, c1), _rows = cell_range(1, 0, n_cells_total)
-    else:     # one grid, sharded by rows
-        (c0, c1), _rows = cell_range(world, rank, n_cells_total)
-    nc = c1 - c0
+    strong = args.scaling == "strong"
+    grid = synthetic.Grid(args.cells, GRID_SEED)
     dates = synthetic.daily_dates(FIRST_YEAR, args.years)
     year, doy, month = _abi.time_axes(dates)
     nd = len(dates)
     n_out = _abi.count_months(year, month)
-
-    # ---- resident workload (value leg) -------------------------------------------------------------
-    cells = build_cells(torch, device, n_cells_total, c0, c1)
-    f_sw = torch.empty((nd, nc), dtype=torch.float32, device=device)
-    f_tc = torch.empty_like(f_sw)
-    f_pn = torch.empty_like(f_sw)
-    fill_forcing(torch, device, cells, doy, 777 + rank, f_sw, f_tc, f_pn)
-    outs = [torch.empty((n_out, nc), dtype=torch.float64, device=device) for _ in range(9)]
-    diag = torch.empty((_abi.SPLASH_NDIAG, nc), dtype=torch.float64, device=device)
-    cptr = {k: v.data_ptr() for k, v in cells.items()}
-    cin = grid_in_struct(nc, nd, year, doy, month, f_sw.data_ptr(), f_tc.data_ptr(), f_pn.data_ptr(), cptr,
-                         _abi.SPLASH_MEM_DEVICE, f32=True)
-    cout = grid_out_struct(n_out, nc, [o.data_ptr() for o in outs], diag.data_ptr(), _abi.SPLASH_MEM_DEVICE)
-    opts = _abi.SplashOpts()
-    opts.monthly_out = 1
+    phases = {}
 
     def barrier():
         torch.cuda.synchronize()
@@ -339,37 +413,66 @@ def main():
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=op)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
         return float(t.item())
 
+    # ---- resident workload (value leg) -------------------------------------------------------------
+    t0 = time.perf_counter()
+    segs = rank_cells(grid, world, rank, strong)
+    if not strong and world > 1:
+        grid = synthetic.Grid(args.cells, GRID_SEED + rank)  # weak: every rank its own forcing realisation
+    shard = Shard(torch, device, grid, segs, doy)
+    nc = shard.nc
+    outs = [torch.empty((n_out, nc), dtype=torch.float64, device=device) for _ in range(9)]
+    diag = torch.empty((_abi.SPLASH_NDIAG, nc), dtype=torch.float64, device=device)
+    cin = grid_in_struct(nc, nd, year, doy, month, shard.f[0].data_ptr(), shard.f[1].data_ptr(), shard.f[2].data_ptr(),
+                         shard.ptrs(), _abi.SPLASH_MEM_DEVICE, f32=True)
+    cout = grid_out_struct(n_out, nc, [o.data_ptr() for o in outs], diag.data_ptr(), _abi.SPLASH_MEM_DEVICE)
+    opts = _abi.SplashOpts()
+    opts.monthly_out = 1
+    torch.cuda.synchronize()
+    phases["generate_s"] = time.perf_counter() - t0
+
     # ---- value: W warm-up + K timed steps, inputs resident -------------------------------------------
+    t0 = time.perf_counter()
     stats_steps = []
     for _ in range(args.warmup):
         ctx.grid_run(cin, opts, cout)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    t0 = time.perf_counter()
+    tv = time.perf_counter()
     for _ in range(args.steps):
         ctx.grid_run(cin, opts, cout)  # synchronous: returns after its streams are drained
         stats_steps.append(ctx.stats())
     barrier()
-    t_value = time.perf_counter() - t0
+    t_value = time.perf_counter() - tv
     clocks = sampler.stop()
-    t_value = allreduce(t_value, dist.ReduceOp.MAX if world > 1 else None)
+    t_value = allreduce(t_value, "max")
     passes = diag[_abi.DIAG_NAMES.index("spin_passes")]
     job_rank = nc * nd + required_spin_days(passes)
-    job_total = allreduce(float(job_rank), dist.ReduceOp.SUM if world > 1 else None)
+    job_total = allreduce(float(job_rank), "sum")
     executed_rank = nc * nd + float(np.mean([s["spin_cell_days"] for s in stats_steps]))
-    executed_total = allreduce(executed_rank, dist.ReduceOp.SUM if world > 1 else None)
+    executed_total = allreduce(executed_rank, "sum")
+    cells_all = allreduce(float(nc), "sum")
     ms_per_step = t_value / args.steps * 1e3
     value = job_total / (t_value / args.steps)
     launches = int(sum(s["kernel_launches"] for s in stats_steps))
     finite_frac = float(torch.isfinite(outs[0]).double().mean().item())
+    phases["value_s"] = time.perf_counter() - t0
 
-    # ---- roofline of the dominant kernel: the bulk daily-integration kernel (k_splash_fused, bulk mode) run
-    #      ALONE over the whole shard -- a resume call (skip_spinup) launches nothing else of weight -- and
-    #      timed with CUDA events on its streams inside the library (splash_stats.bulk_span_ms) --------------
+    # GPU results of the parity sample (rank 0, N == 1: the CPU leg runs the same cells on the reference)
+    sample_got = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        pick = sample_indices(args.cells, args.cpu_sample)  # at N == 1 local index == global index
+        pt = torch.as_tensor(pick, device=device)
+        sample_got = {k: o[:, pt].cpu().numpy() for k, o in zip(_abi.OUTPUT_NAMES, outs)}
+        sample_passes = passes[pt].cpu().numpy()
+
+    # ---- roofline of the dominant kernel: the bulk daily-integration kernel (k_run_bulk) run ALONE over the whole
+    #      shard -- a resume call (skip_spinup) launches nothing else of weight -- and timed with CUDA events on its
+    #      streams inside the library (splash_stats.bulk_span_ms) ---------------------------------------------------
+    t0 = time.perf_counter()
     hbm_peak, hbm_src = peaks()
     dfma_peak, dfma_src = fp64_peak()
     st_dev = torch.empty((_abi.SPLASH_NSTATE, nc), dtype=torch.float64, device=device)
@@ -381,7 +484,8 @@ def main():
     ropts.monthly_out, ropts.skip_spinup = 1, 1
     ropts.state_init = st_host.ctypes.data_as(C.c_void_p)
     spans = []
-    for i in range(1 + max(1, args.steps)):
+    n_roof = min(max(1, args.steps), ROOFLINE_MAX_STEPS)
+    for i in range(1 + n_roof):
         ctx.grid_run(cin, ropts, cout)
         if i:
             spans.append(ctx.stats()["bulk_span_ms"])
@@ -395,7 +499,7 @@ def main():
     hbm_part = {"achieved": hbm_achieved, "peak": hbm_peak, "frac": hbm_achieved / hbm_peak, "unit": "GB/s",
                 "peak_source": hbm_src, "algorithmic_bytes_per_cell_day": alg_bytes_per_cd}
     roofline = {
-        "bound": "fp64", "kernel": "k_splash_fused<bulk> (daily integration of every cell), timed alone",
+        "bound": "fp64", "kernel": "k_run_bulk (daily integration of every cell of the shard), timed alone", "steps": n_roof,
         "unit": "TFLOP/s", "achieved": None, "peak": 2 * dfma_peak / 1e12, "frac": None, "traffic": None,
         "peak_source": dfma_src, "fp64_inst_per_cell_day": inst_cd, "flops_per_cell_day": flops_cd, "work_source": work_src,
         "kernel_ms_per_launch": bulk_ms / bulk_launches, "launches_per_pass": bulk_launches,
@@ -413,114 +517,177 @@ def main():
         roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_cell_day")
         if roofline["traffic"] is not None:
             roofline["traffic"] = roofline["traffic"] * bulk_cell_days / bulk_launches
-    del st_dev
+    shard_index, shard_cells_np, filler = shard.index, shard.cells_np, shard.filler
+    del st_dev, cout, cout_st, outs, diag, shard, cin   # the resident forcing is not needed any more
+    torch.cuda.empty_cache()
+    phases["roofline_s"] = time.perf_counter() - t0
 
-    # ---- e2e: the same job through the C ABI with pinned HOST buffers, block of rows by block ----------
+    # ---- e2e: the same job through the C ABI with pinned HOST buffers, row blocks through the block scheduler ----
     e2e = None
     if not args.no_e2e:
-        # the value leg's output layers are not needed any more (the forcing stays: the host blocks are staged from it)
-        del cout, cout_st, outs, diag
-        torch.cuda.empty_cache()
-        # pinned f64 forcing per block: <= ~72 GB, and the ranks of a box share its host memory
-        pin_budget = 72e9
+        t0 = time.perf_counter()
+        ctx.close()  # the lanes of the cluster own the device from here on
+        # pinned f64 forcing: at most ~45 % of what the host has free, shared by the ranks of the box
+        pin_budget = 110e9
         try:
             avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
-            pin_budget = min(pin_budget, 0.38 * avail / world)
+            pin_budget = min(pin_budget, 0.45 * avail / world)
         except Exception:
             pass
-        n_blocks = args.e2e_blocks or max(1, int(np.ceil(nc * nd * 3 * 8 / pin_budget)))
-        bsz = int(np.ceil(nc / n_blocks / 1024) * 1024)
+        lanes = max(1, args.e2e_lanes)
+        n_buf = lanes + 1                                   # blocks staged at a time = blocks per pipelined group
+        per_cell = nd * 3 * 8 + n_out * 9 * 8 + 14 * 8
+        bsz = int(min(nc, max(1024, (pin_budget / n_buf / per_cell) // 1024 * 1024)))
+        if args.e2e_blocks:
+            bsz = int(np.ceil(nc / args.e2e_blocks / 1024) * 1024)
+        else:  # equal blocks, a whole number of groups
+            n_groups = int(np.ceil(nc / (bsz * n_buf)))
+            bsz = int(np.ceil(nc / (n_groups * n_buf) / 1024) * 1024)
         n_blocks = int(np.ceil(nc / bsz))
-        h_f = [torch.empty((nd, bsz), dtype=torch.float64).pin_memory() for _ in range(3)]
-        h_cells = {k: torch.empty(v.shape[:-1] + (bsz,), dtype=torch.float64).pin_memory() for k, v in cells.items()}
-        h_out = [torch.empty((n_out, bsz), dtype=torch.float64).pin_memory() for _ in range(9)]
-        h_diag = torch.empty((_abi.SPLASH_NDIAG, bsz), dtype=torch.float64).pin_memory()
+        pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        bufs = [{"f": [pin(nd, bsz) for _ in range(3)], "out": [pin(n_out, bsz) for _ in range(9)],
+                 "cells": {k: np.zeros((v.shape[0], bsz) if v.ndim == 2 else (bsz,)) for k, v in shard_cells_np.items()
+                           if k in ("lat", "elev", "slop", "asp", "resolution", "soil", "au")}} for _ in range(min(n_buf, n_blocks))]
+        chunk_days = max(1, int(2e9 // (bsz * 8 * 3)))
+        d_chunk = [torch.empty((chunk_days, bsz), dtype=torch.float64, device=device) for _ in range(3)]
         hopts = _abi.SplashOpts()
         hopts.monthly_out = 1
+        phases["e2e_alloc_s"] = time.perf_counter() - t0
 
+        def stage(b, buf):
+            """block b's inputs into pinned host memory (untimed: this is the caller's data)"""
+            b0, b1 = b * bsz, min(nc, (b + 1) * bsz)
+            n = b1 - b0
+            idx = shard_index[b0:b1]
+            # contiguous runs of global cells inside the block (shard boundaries of the round-robin deal)
+            cuts = np.flatnonzero(np.diff(idx) != 1) + 1
+            runs = np.split(np.arange(n), cuts)
+            for d0 in range(0, nd, chunk_days):
+                d1 = min(nd, d0 + chunk_days)
+                for r in runs:
+                    sub = {k: (v[..., b0 + r[0]:b0 + r[-1] + 1] if isinstance(v, np.ndarray) else v) for k, v in shard_cells_np.items()}
+                    filler.fill(sub, d_chunk[0][:, r[0]:], d_chunk[1][:, r[0]:], d_chunk[2][:, r[0]:], day0=d0, n_days=d1 - d0)
+                for h, dsrc in zip(buf["f"], d_chunk):
+                    h[d0:d1, :n].copy_(dsrc[:d1 - d0, :n])
+            for k, v in buf["cells"].items():
+                v[..., :n] = shard_cells_np[k][..., b0:b1]
+            torch.cuda.synchronize()
+            return n
+
+        def structs(buf, n):
+            hp = {k: v.ctypes.data for k, v in buf["cells"].items()}
+            bin_ = grid_in_struct(n, nd, year, doy, month, buf["f"][0].data_ptr(), buf["f"][1].data_ptr(), buf["f"][2].data_ptr(), hp,
+                                  _abi.SPLASH_MEM_HOST, f32=False)
+            bin_.cell_stride = bsz
+            bin_.attr_stride = bsz
+            bout = grid_out_struct(n_out, n, [o.data_ptr() for o in buf["out"]], None, _abi.SPLASH_MEM_HOST)
+            bout.cell_stride = bsz
+            return bin_, bout
+
+        n_e2e = min(max(1, args.steps), E2E_MAX_STEPS)
+        t_steps = np.zeros(n_e2e)
+        h2d_b = d2h_b = 0
         block_stats = []
-
-        def run_blocks(timed: bool):
-            tot = 0.0
-            block_stats.clear()
-            h2d = d2h = 0
-            nl = 0
-            for b in range(n_blocks):
-                b0, b1 = b * bsz, min(nc, (b + 1) * bsz)
-                n = b1 - b0
-                # stage the block's inputs in pinned host memory (untimed: this is the caller's data)
-                for h, dsrc in zip(h_f, (f_sw, f_tc, f_pn)):
-                    h[:, :n].copy_(dsrc[:, b0:b1])
-                for k in h_cells:
-                    h_cells[k][..., :n].copy_(cells[k][..., b0:b1])
+        cl = Cluster([local_rank], lanes)
+        first = True
+        barrier()  # the ranks start their host-fed passes together (they share the host's memory and PCIe fabric)
+        for g0 in range(0, n_blocks, len(bufs)):
+            grp = list(range(g0, min(n_blocks, g0 + len(bufs))))
+            ns = [stage(b, bufs[i]) for i, b in enumerate(grp)]
+            st = [structs(bufs[i], n) for i, n in enumerate(ns)]
+            for rep in range((1 if first else 0) + n_e2e):   # one untimed pass of the first group sizes the lanes' buffers
+                timed = rep >= (1 if first else 0)
                 torch.cuda.synchronize()
-                hp = {k: v.data_ptr() for k, v in h_cells.items()}
-                bin_ = grid_in_struct(n, nd, year, doy, month, h_f[0].data_ptr(), h_f[1].data_ptr(), h_f[2].data_ptr(), hp,
-                                      _abi.SPLASH_MEM_HOST, f32=False)
-                bin_.cell_stride = bsz
-                # per-cell host arrays are [k, bsz] with pitch bsz: pass the strided soil/au through a compact copy
-                soil_c = h_cells["soil"][:, :n].contiguous()
-                au_c = h_cells["au"][:, :n].contiguous()
-                bin_.soil, bin_.au = soil_c.data_ptr(), au_c.data_ptr()
-                bout = grid_out_struct(n_out, n, [o.data_ptr() for o in h_out], h_diag.data_ptr(), _abi.SPLASH_MEM_HOST)
-                bout.cell_stride = bsz
-                bout.cell_diag = None
                 t = time.perf_counter()
-                ctx.grid_run(bin_, hopts, bout)
-                tot += time.perf_counter() - t
-                s = ctx.stats()
-                h2d += s["h2d_bytes"]
-                d2h += s["d2h_bytes"]
-                nl += s["kernel_launches"]
-                block_stats.append({k: s[k] for k in ("total_ms", "gpu_ms", "h2d_ms", "d2h_ms", "pool_wait_ms", "scatter_ms", "first_ms",
-                                                      "rounds_ms", "bulk_ms", "n_tiles", "tile_cells", "pool_cells", "pool_max_passes")})
-            return tot, h2d, d2h, nl
+                tickets = [cl.submit(bi, hopts, bo) for bi, bo in st]
+                res = [cl.wait(tk) for tk in tickets]
+                dt = time.perf_counter() - t
+                if timed:
+                    k = rep - (1 if first else 0)
+                    t_steps[k] += dt
+                    if k == n_e2e - 1:
+                        for _, s in res:
+                            h2d_b += s["h2d_bytes"]
+                            d2h_b += s["d2h_bytes"]
+                            block_stats.append({q: s[q] for q in ("total_ms", "gpu_ms", "h2d_ms", "d2h_ms", "pool_wait_ms", "scatter_ms",
+                                                                  "first_ms", "rounds_ms", "bulk_ms", "n_tiles", "tile_cells", "pool_cells",
+                                                                  "pool_max_passes")})
+                    launches += sum(s["kernel_launches"] for _, s in res)
+            first = False
+        cl.close()
+        t_e2e = allreduce(float(t_steps.mean()), "max")
+        e2e = {"value": job_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+               "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "row_blocks": n_blocks, "blocks_per_group": len(bufs), "lanes": lanes,
+               "host_buffers": "pinned f64 (what R's REAL() holds), day-major; each block staged once, groups of blocks in flight "
+                               "through splash_cluster_submit / _wait (the reference's sendCall / recvOneData)",
+               "block_stats_last_step": block_stats}
+        del bufs, d_chunk
+        torch.cuda.empty_cache()
+        phases["e2e_s"] = time.perf_counter() - t0
+        ctx = Context(local_rank)
 
-        for _ in range(min(args.warmup, 1)):
-            run_blocks(False)
+    # ---- weak-scaling figure beside the strong one (N > 1): one whole grid per rank ------------------------
+    weak_value = None
+    if world > 1 and strong and not args.no_weak:
+        t0 = time.perf_counter()
+        wgrid = synthetic.Grid(args.cells, GRID_SEED + 1000 + rank)
+        wshard = Shard(torch, device, wgrid, [(0, wgrid.n_cells)], doy)
+        wn = wshard.nc
+        wouts = [torch.empty((n_out, wn), dtype=torch.float64, device=device) for _ in range(9)]
+        wdiag = torch.empty((_abi.SPLASH_NDIAG, wn), dtype=torch.float64, device=device)
+        win = grid_in_struct(wn, nd, year, doy, month, wshard.f[0].data_ptr(), wshard.f[1].data_ptr(), wshard.f[2].data_ptr(),
+                             wshard.ptrs(), _abi.SPLASH_MEM_DEVICE, f32=True)
+        wout = grid_out_struct(n_out, wn, [o.data_ptr() for o in wouts], wdiag.data_ptr(), _abi.SPLASH_MEM_DEVICE)
+        ctx.grid_run(win, opts, wout)
         barrier()
-        t_e2e, h2d_b, d2h_b = 0.0, 0, 0
-        for _ in range(args.steps):
-            tt, hb, db, nl = run_blocks(True)
-            t_e2e += tt
-            h2d_b, d2h_b = hb, db
-            launches += nl
+        tw = time.perf_counter()
+        for _ in range(2):
+            ctx.grid_run(win, opts, wout)
         barrier()
-        t_e2e = allreduce(t_e2e, dist.ReduceOp.MAX if world > 1 else None)
-        e2e = {"value": job_total / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
-               "d2h_bytes_per_step": int(d2h_b), "ms_per_step": t_e2e / args.steps * 1e3, "row_blocks": n_blocks,
-               "host_buffers": "pinned f64 (what R's REAL() holds), day-major", "block_stats_last_step": list(block_stats)}
-        del h_f, h_out
+        t_weak = allreduce(time.perf_counter() - tw, "max")
+        wjob = allreduce(float(wn * nd + required_spin_days(wdiag[_abi.DIAG_NAMES.index("spin_passes")])), "sum")
+        weak_value = wjob / (t_weak / 2)
+        del wshard, wouts, wdiag
+        phases["weak_s"] = time.perf_counter() - t0
 
-    # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
+    # ---- CPU baseline beside it, and the parity of the benchmark grid's own cells (rank 0, N == 1 only) ----------
     cpu = None
+    parity_rep = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        t0 = time.perf_counter()
         try:
-            _, _, cpu = cpu_leg(args.cpu_sample, args.years)
+            _, _, cpu, prob, pick, ref = cpu_leg(args.cpu_sample, args.years, n_cells=args.cells)
+            if sample_got is not None:
+                parity_rep = parity_block(prob, ref, sample_got, sample_passes)
         except Exception as e:  # the checker is optional for the measurement itself
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        phases["cpu_s"] = time.perf_counter() - t0
 
     if rank == 0:
+        phases["total_s"] = time.perf_counter() - t_start
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"synthetic 5-arcmin global grid ({n_cells_total} land cells) x {args.years} years daily "
+                "workload": f"synthetic 5-arcmin global grid ({args.cells} land cells) x {args.years} years daily "
                             f"({nd} days) incl. spin-up, monthly outputs (BASELINE.json configs[3])",
-                "cells_total": n_cells_total, "cells_rank0": nc, "n_days": nd, "n_out_layers": 9, "n_months": n_out,
-                "parallelism": (f"{world} rank(s), one 5-arcmin grid (own forcing realisation) per rank, no data-path collective"
-                                if weak else f"one grid, rows sharded over {world} rank(s), no data-path collective"),
-                "cells_all_ranks": n_cells_total * (world if weak else 1),
+                "cells_total": int(cells_all), "cells_rank0": nc, "n_days": nd, "n_out_layers": 9, "n_months": n_out,
+                "parallelism": (f"one grid, blocks of {ROW_BLOCK} grid rows dealt round-robin to {world} rank(s), no data-path collective"
+                                if strong else f"{world} rank(s), one whole grid (own forcing realisation) per rank, no data-path collective"),
+                "generator": f"counter-based splitmix64(seed {GRID_SEED}, cell, day, field): shards, row blocks and the CPU sample are subsets of one grid",
                 "forcing_hbm_dtype": "f32 (lossless: values are FP32-representable like the FLT4S rasters)",
                 "l2": "inputs per step (>= 10 GB per rank) are far larger than the 126 MB L2",
                 "job_cell_days": job_total, "executed_cell_days": executed_total,
-                "spin_share_of_job": 1.0 - n_cells_total * (world if weak else 1) * nd / job_total,
+                "executed_cell_days_per_s": executed_total / (ms_per_step * 1e-3),
+                "spin_share_of_job": 1.0 - cells_all * nd / job_total,
                 "finite_fraction_wn": finite_frac,
                 # SURVEY 8(d): the series days alone over the same wall time, so that spin-up pass counts do not blur it
-                "nd_only_cell_days_per_s": n_cells_total * (world if weak else 1) * nd / (ms_per_step * 1e-3),
+                "nd_only_cell_days_per_s": cells_all * nd / (ms_per_step * 1e-3),
+                "weak_value": weak_value if weak_value is not None else (value if world == 1 or not strong else None),
+                "phases_s": {k: round(v, 1) for k, v in phases.items()},
             },
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity_rep, "e2e": e2e, "gpu_launches": launches,
             "stats_last_step": stats_steps[-1],
         }
         print(json.dumps(line), flush=True)

@@ -30,6 +30,20 @@
  * context.  A context is bound to one CUDA device and is not re-entrant: one call at a time.
  * There is no CPU fallback: without a usable CUDA device splash_ctx_create fails.
  *
+ *   splash_cluster_*  <- the block scheduler of splash.grid over its N workers: sendCall(cl[[i]], clFun, i)
+ *                        for the first `nodes` blocks, then recvOneData() / sendCall() of the next block until
+ *                        all blocks are in (R/splash.grid.R:264-268, 312-314, 359-400).  A cluster is a set of
+ *                        lanes (GPUs x calls in flight per GPU); submit == sendCall, wait == recvOneData.
+ *   splash_ctx_create_multi <- the same scheduler driven by the library itself: splash_grid_run on such a
+ *                        context cuts the call into row blocks (two per lane, like blockSize(minblocks =
+ *                        nodes * 2), :264-268), runs them over all its GPUs and writes disjoint ranges of the
+ *                        caller's arrays.  Cells are independent: there is no data-path collective and no NCCL.
+ *
+ * Process environment: a call keeps ~26 CUDA streams busy; with CUDA's default of 8 hardware work queues
+ * streams share queues and kernels of one stream wait behind seconds-long kernels of another.  Export
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 before the process initialises CUDA (the library does not touch the
+ * environment; rsplash_b200/__init__.py and the R shim in INTEGRATION.md do it for their processes).
+ *
  * NaN inputs are data, not errors: they propagate exactly as in the reference (per-layer NA masks).
  */
 #ifndef SPLASH_CUDA_H
@@ -41,8 +55,8 @@
 extern "C" {
 #endif
 
-#define SPLASH_ABI_VERSION 4
-#define SPLASH_NSTATE 6
+#define SPLASH_ABI_VERSION 5
+#define SPLASH_NSTATE 7
 
 /* status codes */
 enum {
@@ -101,6 +115,8 @@ typedef struct splash_grid_in {
     int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE: applies to every pointer above except year/doy/month (always host) */
     int32_t forcing_dtype;  /* SPLASH_F64 (what R passes) or SPLASH_F32 (rasters are FLT4S on disk) */
     int32_t reserved;
+    int64_t attr_stride;    /* elements between consecutive layers of soil and au; 0 means n_cells (a block that is a
+                             * column range of a larger matrix passes the matrix's cell count) */
 } splash_grid_in;
 
 /* Outputs: the nine layers of R/splash.grid.R:449 (any pointer may be NULL = not wanted). */
@@ -116,12 +132,15 @@ typedef struct splash_grid_out {
     double* bflow;          /* lateral drainage, mm */
     double* netr;           /* daytime net radiation, MJ m-2 */
     double* sm_lim;         /* relative soil moisture limitation 0..1 */
-    double* state_final;    /* optional [SPLASH_NSTATE*n_cells] layer-major: wn, snow, qin, td, nd after the last day (the carried
-                             * arguments of run_all, SPLASH.cpp:1833-1835) and the value of soil_info[12] (the aridity index
-                             * R/splash.point.R:150 writes there): everything a later call needs to continue the series */
-    double* cell_diag;      /* optional [SPLASH_NDIAG*n_cells] layer-major */
+    double* state_final;    /* optional [SPLASH_NSTATE*aux_stride] layer-major: wn, snow, qin, td, nd after the last day (the carried
+                             * arguments of run_all, SPLASH.cpp:1833-1835), the value of soil_info[12] (the aridity index
+                             * R/splash.point.R:150 writes there) and the snowfall threshold temperature Tt the series was
+                             * partitioned with (a reduction over the WHOLE tc series, R/splash.point.R:120-122, which a
+                             * later segment cannot recompute): everything a later call needs to continue the series */
+    double* cell_diag;      /* optional [SPLASH_NDIAG*aux_stride] layer-major */
     int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE for every pointer above */
     int32_t reserved;
+    int64_t aux_stride;     /* elements between consecutive layers of state_final and cell_diag; 0 means n_cells */
 } splash_grid_out;
 
 typedef struct splash_opts {
@@ -131,7 +150,10 @@ typedef struct splash_opts {
     int64_t tile_cells;     /* cells per device tile; 0 = choose from free device memory */
     int32_t skip_spinup;    /* 1 = start run_all from state_init instead of spinning up (resume) */
     int32_t reserved;
-    const double* state_init; /* [SPLASH_NSTATE*n_cells] layer-major, a previous call's state_final (host); used when skip_spinup */
+    const double* state_init; /* [SPLASH_NSTATE*state_stride] layer-major, a previous call's state_final (host); used when
+                               * skip_spinup.  The resumed segment is partitioned into rain and snow with the carried Tt
+                               * (row 6), so that a series run in pieces equals the series run at once */
+    int64_t state_stride;   /* elements between consecutive layers of state_init; 0 means n_cells */
 } splash_opts;
 
 /* Timing / accounting of the last call, filled by splash_last_stats (all times in milliseconds).
@@ -168,7 +190,13 @@ int splash_abi_version(void);
 /* Create a context on CUDA device `device` (ordinal).  Fails with SPLASH_ERR_NO_DEVICE when there
  * is no CUDA device: the library has no host implementation of the model. */
 int splash_ctx_create(int device, splash_ctx** out_ctx);
+/* A context over several GPUs of one host.  splash_grid_run / splash_point_run on it accept HOST
+ * arrays only; the call is cut into row blocks that are scheduled over the devices (see splash_cluster_*),
+ * every block writes its own cell range of the caller's arrays.  n_devices == 1 is allowed. */
+int splash_ctx_create_multi(const int* devices, int n_devices, splash_ctx** out_ctx);
 void splash_ctx_destroy(splash_ctx* ctx);
+/* Number of GPUs behind a context (1 for splash_ctx_create). */
+int splash_ctx_device_count(const splash_ctx* ctx);
 
 /* Message of the last failure on this context (or of the last failed splash_ctx_create when ctx is
  * NULL).  Never NULL; valid until the next call on the same context. */
@@ -191,8 +219,27 @@ int splash_point_run(splash_ctx* ctx, int64_t n_days, const int32_t* year, const
                      const double* au, int32_t au_len, double resolution, const splash_opts* opts,
                      splash_grid_out* out);
 
-/* Accounting of the last splash_grid_run / splash_point_run on this context. */
+/* Accounting of the last splash_grid_run / splash_point_run on this context (multi-GPU contexts: byte, cell-day
+ * and launch counts summed over the blocks, times are the maximum over the lanes). */
 int splash_last_stats(const splash_ctx* ctx, splash_stats* out);
+
+/* ---- block scheduler: the reference's sendCall / recvOneData loop (R/splash.grid.R:312-314, 359-400) ----
+ * A cluster owns `lanes_per_device` single-GPU contexts on each listed device, each with a worker thread.
+ * submit() hands a block (HOST arrays, which must stay valid and untouched until the block has been waited
+ * for) to the least-loaded lane and returns at once with a ticket; wait() blocks until the given ticket (or,
+ * with ticket < 0, any outstanding one) has finished and returns its status, ticket and accounting.  With two
+ * lanes per device the upload of block k+1 overlaps the tail of block k (its last stragglers' spin-up chain),
+ * which a sequence of synchronous splash_grid_run calls leaves exposed. */
+typedef struct splash_cluster splash_cluster;
+int splash_cluster_create(const int* devices, int n_devices, int lanes_per_device, splash_cluster** out);
+void splash_cluster_destroy(splash_cluster* cl);
+int splash_cluster_lanes(const splash_cluster* cl);
+int splash_cluster_submit(splash_cluster* cl, const splash_grid_in* in, const splash_opts* opts, const splash_grid_out* out,
+                          int64_t* ticket);
+/* Returns the block's status code (SPLASH_OK, ...) or SPLASH_ERR_BAD_ARG when nothing is outstanding.
+ * done_ticket / stats may be NULL. */
+int splash_cluster_wait(splash_cluster* cl, int64_t ticket, int64_t* done_ticket, splash_stats* stats);
+const char* splash_cluster_last_error(const splash_cluster* cl);
 
 /* ---- unSWC.grid: unsaturated-zone diagnostics of the simulated soil water (R/unsSWC.grid.R:14-141) ----
  * Replaces the four raster::overlay() passes of unSWC.grid (calc_thetai :96-103, calcwtd :112-121, UnsWater

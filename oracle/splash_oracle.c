@@ -1093,8 +1093,18 @@ double splash_oracle_snowfall_prob(double tc, double lat, double elev) {
 }
 
 /* Snow partition, R/splash.point.R:120-128 with frain_func :521-558 (Tr = 13.3). */
+/* Tt_given: NULL = compute Tt from this series (splash.point.R:122); otherwise the threshold carried from the
+ * series' earlier segment (resume: the reduction runs over the WHOLE series, which a later segment cannot redo) */
+static void snow_partition_tt(int n, const double* tc, const double* pn, const int* month, double lat, double elev,
+                              double* rain, double* snowfall, double* Tt_out, const double* Tt_given);
+
 void splash_oracle_snow_partition(int n, const double* tc, const double* pn, const int* month, double lat, double elev,
                                   double* rain, double* snowfall, double* Tt_out) {
+    snow_partition_tt(n, tc, pn, month, lat, elev, rain, snowfall, Tt_out, NULL);
+}
+
+static void snow_partition_tt(int n, const double* tc, const double* pn, const int* month, double lat, double elev,
+                              double* rain, double* snowfall, double* Tt_out, const double* Tt_given) {
     /* Tt <- max(tc[p_snow >= 0.5]): an NA in p_snow yields an NA element, hence NA; an empty
      * selection yields -Inf (with a warning). */
     double Tt = -INFINITY;
@@ -1108,6 +1118,7 @@ void splash_oracle_snow_partition(int n, const double* tc, const double* pn, con
         }
     }
     if (any_na) Tt = NAN;
+    if (Tt_given) Tt = *Tt_given;
     const double Tr = 13.3;
     for (int i = 0; i < n; i++) {
         double p = splash_oracle_snowfall_prob(tc[i], lat, elev);
@@ -1192,6 +1203,10 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
     const int64_t istride = in->cell_stride ? in->cell_stride : in->n_cells;
     const int64_t ostride = out->cell_stride ? out->cell_stride : in->n_cells;
     const int64_t nc = in->n_cells;
+    const int64_t apitch = in->attr_stride ? in->attr_stride : nc;   /* soil, au */
+    const int64_t xpitch = out->aux_stride ? out->aux_stride : nc;   /* state_final, cell_diag */
+    const int64_t spitch = (w->opts && w->opts->state_stride) ? w->opts->state_stride : nc;
+    const int resume = (w->opts && w->opts->skip_spinup && w->opts->state_init);
     const int max_spin = (w->opts && w->opts->max_spin > 0) ? w->opts->max_spin : 1000;
     (void)max_spin; /* the compiled cores hard-wire 1000 passes / 1.0 mm like the reference */
 
@@ -1216,9 +1231,9 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
 
     /* soil hydrophysics and soil_info, R/splash.point.R:96-115 */
     double sh[11];
-    splash_oracle_soil_hydro(in->soil[0 * nc + c], in->soil[1 * nc + c], in->soil[2 * nc + c], in->soil[3 * nc + c],
-                             in->soil[4 * nc + c], sh);
-    double depth = in->soil[5 * nc + c];
+    splash_oracle_soil_hydro(in->soil[0 * apitch + c], in->soil[1 * apitch + c], in->soil[2 * apitch + c], in->soil[3 * apitch + c],
+                             in->soil[4 * apitch + c], sh);
+    double depth = in->soil[5 * apitch + c];
     double SAT = sh[0] * depth * 1000;
     double WP = sh[2] * depth * 1000;
     double FC = sh[1] * depth * 1000;
@@ -1244,8 +1259,8 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
         soil_info[12] = NAN; /* not part of the R vector (length 12) */
         n_si = 12;
     } else {
-        soil_info[10] = in->au[1 * nc + c];
-        soil_info[11] = in->au[2 * nc + c];
+        soil_info[10] = in->au[1 * apitch + c];
+        soil_info[11] = in->au[2 * apitch + c];
         soil_info[12] = 1;
         n_si = 13;
     }
@@ -1253,7 +1268,8 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
     /* snow partition, :120-128; aspect convention, :131 */
     double Tt;
     int* month32 = (int*)in->month;
-    splash_oracle_snow_partition((int)nd, tc, pn, month32, lat, elev, rain, snowfall, &Tt);
+    snow_partition_tt((int)nd, tc, pn, month32, lat, elev, rain, snowfall, &Tt,
+                      resume ? &w->opts->state_init[6 * spitch + c] : NULL);
     double asp = in->asp[c] - 180;
 
     /* first-year spin-up inputs, :141-147 (x[1:365] pads with NA when the series is shorter) */
@@ -1270,14 +1286,14 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
     double wn_last, snow_last, qin_last, td_last, nds_last;
     double AI = NAN;
     int passes = 0;
-    if (w->opts && w->opts->skip_spinup && w->opts->state_init) {
+    if (resume) {
         const double* st = w->opts->state_init;
-        wn_last = st[0 * nc + c];
-        snow_last = st[1 * nc + c];
-        qin_last = st[2 * nc + c];
-        td_last = st[3 * nc + c];
-        nds_last = st[4 * nc + c];
-        soil_info[11] = st[5 * nc + c]; /* the aridity index the interrupted run had put there, splash.point.R:150 */
+        wn_last = st[0 * spitch + c];
+        snow_last = st[1 * spitch + c];
+        qin_last = st[2 * spitch + c];
+        td_last = st[3 * spitch + c];
+        nds_last = st[4 * spitch + c];
+        soil_info[11] = st[5 * spitch + c]; /* the aridity index the interrupted run had put there, splash.point.R:150 */
         AI = soil_info[11];
     } else {
         int y1 = in->year[0];
@@ -1338,28 +1354,29 @@ static void run_cell(work_t* w, int64_t c, double* buf) {
     }
     if (out->state_final) {
         double* st = out->state_final;
-        st[0 * nc + c] = nd ? o[0][nd - 1] : wn_last;
-        st[1 * nc + c] = nd ? o[4][nd - 1] : snow_last;
-        st[2 * nc + c] = nd ? o[8][nd - 1] : qin_last;
-        st[3 * nc + c] = nd ? o[9][nd - 1] : td_last;
-        st[4 * nc + c] = nd ? o[10][nd - 1] : nds_last;
-        st[5 * nc + c] = soil_info[11];
+        st[0 * xpitch + c] = nd ? o[0][nd - 1] : wn_last;
+        st[1 * xpitch + c] = nd ? o[4][nd - 1] : snow_last;
+        st[2 * xpitch + c] = nd ? o[8][nd - 1] : qin_last;
+        st[3 * xpitch + c] = nd ? o[9][nd - 1] : td_last;
+        st[4 * xpitch + c] = nd ? o[10][nd - 1] : nds_last;
+        st[5 * xpitch + c] = soil_info[11];
+        st[6 * xpitch + c] = Tt;
     }
     if (out->cell_diag) {
         double* dg = out->cell_diag;
-        for (int k = 0; k < 8; k++) dg[(int64_t)k * nc + c] = soil_info[k];
-        dg[SPLASH_DIAG_WMAX_R * nc + c] = Wmax;
-        dg[SPLASH_DIAG_TT * nc + c] = Tt;
-        dg[SPLASH_DIAG_AI * nc + c] = AI;
-        dg[SPLASH_DIAG_SPIN_PASSES * nc + c] = passes;
+        for (int k = 0; k < 8; k++) dg[(int64_t)k * xpitch + c] = soil_info[k];
+        dg[SPLASH_DIAG_WMAX_R * xpitch + c] = Wmax;
+        dg[SPLASH_DIAG_TT * xpitch + c] = Tt;
+        dg[SPLASH_DIAG_AI * xpitch + c] = AI;
+        dg[SPLASH_DIAG_SPIN_PASSES * xpitch + c] = passes;
         int nsnow = 0, nsf = 0;
         for (int64_t d = 0; d < nd; d++) {
             double p = splash_oracle_snowfall_prob(tc[d], lat, elev);
             if (p >= 0.5) nsnow++;
             if (snowfall[d] > 0.0) nsf++;
         }
-        dg[SPLASH_DIAG_SNOW_DAYS * nc + c] = nsnow;
-        dg[SPLASH_DIAG_SNOWFALL_DAYS * nc + c] = nsf;
+        dg[SPLASH_DIAG_SNOW_DAYS * xpitch + c] = nsnow;
+        dg[SPLASH_DIAG_SNOWFALL_DAYS * xpitch + c] = nsf;
     }
 }
 

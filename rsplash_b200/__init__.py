@@ -6,11 +6,11 @@ The package is a thin host mirror of the reference's R interface over libsplash_
 from . import _abi  # noqa: F401
 from ._abi import OUTPUT_NAMES  # noqa: F401
 
-__all__ = ["splash_grid", "splash_point", "Context", "SplashError", "OUTPUT_NAMES"]
+__all__ = ["splash_grid", "splash_point", "Context", "Cluster", "SplashError", "OUTPUT_NAMES"]
 
 
 def __getattr__(name):
-    if name in ("splash_grid", "splash_point", "Context", "SplashError", "default_context"):
+    if name in ("splash_grid", "splash_point", "Context", "Cluster", "SplashError", "default_context"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

@@ -9,8 +9,8 @@ import ctypes as C
 
 import numpy as np
 
-SPLASH_ABI_VERSION = 4
-SPLASH_NSTATE = 6
+SPLASH_ABI_VERSION = 5
+SPLASH_NSTATE = 7
 
 SPLASH_OK, SPLASH_ERR_BAD_ARG, SPLASH_ERR_CUDA, SPLASH_ERR_NOMEM, SPLASH_ERR_NO_DEVICE = range(5)
 SPLASH_MEM_HOST, SPLASH_MEM_DEVICE = 0, 1
@@ -26,7 +26,7 @@ SPLASH_NDIAG = len(DIAG_NAMES)
 OUTPUT_NAMES = ("wn", "ro", "pet", "aet", "snow", "cond", "bflow", "netr", "sm_lim")
 # monthly aggregation rule, R/splash.point.R:210-211
 MONTHLY_MEAN = ("wn", "snow", "sm_lim")
-STATE_NAMES = ("wn", "snow", "qin", "td", "nd")
+STATE_NAMES = ("wn", "snow", "qin", "td", "nd")  # rows 0..4 of state_final; row 5 the aridity index, row 6 Tt
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -54,6 +54,7 @@ class SplashGridIn(C.Structure):
         ("mem_kind", C.c_int32),
         ("forcing_dtype", C.c_int32),
         ("reserved", C.c_int32),
+        ("attr_stride", C.c_int64),
     ]
 
 
@@ -74,6 +75,7 @@ class SplashGridOut(C.Structure):
         ("cell_diag", C.c_void_p),
         ("mem_kind", C.c_int32),
         ("reserved", C.c_int32),
+        ("aux_stride", C.c_int64),
     ]
 
 
@@ -86,6 +88,7 @@ class SplashOpts(C.Structure):
         ("skip_spinup", C.c_int32),
         ("reserved", C.c_int32),
         ("state_init", C.c_void_p),
+        ("state_stride", C.c_int64),
     ]
 
 

@@ -18,15 +18,17 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from . import _abi
-from ._lib import Context, SplashError  # noqa: F401
+from ._lib import Cluster, Context, SplashError  # noqa: F401
 
-_default_ctx: dict[int, Context] = {}
+_default_ctx: dict = {}
 
 
-def default_context(device: int = 0) -> Context:
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+def default_context(device=0) -> Context:
+    """The process-wide context of a device (or of a tuple of devices: a multi-GPU context)."""
+    key = tuple(device) if isinstance(device, (list, tuple)) else device
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(list(key) if isinstance(key, tuple) else key)
+    return _default_ctx[key]
 
 
 def _f64(a, shape=None, name=""):
@@ -124,21 +126,45 @@ def splash_grid(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, 
 
 
 def splash_point(sw_in, tc, pn, lat, elev, slop=0.0, asp=0.0, soil_data=None, Au=0.0, resolution=250.0,
-                 time_index=None, monthly_out: bool = False, ctx: Context | None = None, **kw) -> dict:
+                 time_index=None, monthly_out: bool = False, ctx: Context | None = None, return_state: bool = False,
+                 return_diag: bool = False) -> dict:
     """splash.point(sw_in, tc, pn, lat, elev, slop, asp, soil_data, Au, resolution, time_index, monthly_out).
 
-    One cell; same defaults as the R function (R/splash.point.R:29).  Returns {layer: [n_out]}.
+    One cell through the C entry `splash_point_run`; same defaults as the R function (R/splash.point.R:29).
+    Returns {layer: [n_out]}.
     """
     if soil_data is None or time_index is None:
         raise ValueError("soil_data and time_index are required")
-    au = np.atleast_1d(np.asarray(Au, dtype=np.float64))
+    ctx = ctx or default_context()
+    au = np.ascontiguousarray(np.atleast_1d(np.asarray(Au, dtype=np.float64)))
     if au.size not in (1, 3):
         raise ValueError("Au must have 1 or 3 elements")
-    col = lambda a: np.asarray(a, dtype=np.float64).reshape(-1, 1)
-    res = splash_grid(col(sw_in), col(tc), col(pn), [lat], [elev], [slop], [asp],
-                      np.asarray(soil_data, dtype=np.float64).reshape(6, 1), au.reshape(-1, 1), [resolution],
-                      time_index, monthly_out=monthly_out, ctx=ctx, **kw)
-    return {k: (v[:, 0] if isinstance(v, np.ndarray) and v.ndim == 2 else v) for k, v in res.items()}
+    vec = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    sw_in, tc, pn = vec(sw_in), vec(tc), vec(pn)
+    soil = vec(soil_data)
+    if soil.size != 6:
+        raise ValueError("soil_data must have six elements")
+    year, doy, month = _abi.time_axes(time_index)
+    n_days = len(year)
+    if not (len(sw_in) == len(tc) == len(pn) == n_days):
+        raise ValueError("sw_in, tc, pn and time_index must have the same length")
+    n_out = _abi.count_months(year, month) if monthly_out else n_days
+    result = {k: np.empty(n_out) for k in _abi.OUTPUT_NAMES}
+    cout = _abi.SplashGridOut()
+    cout.n_out, cout.cell_stride, cout.mem_kind = n_out, 1, _abi.SPLASH_MEM_HOST
+    for k in _abi.OUTPUT_NAMES:
+        setattr(cout, k, _ptr(result[k]))
+    if return_state:
+        result["state_final"] = np.empty(_abi.SPLASH_NSTATE)
+        cout.state_final = _ptr(result["state_final"])
+    if return_diag:
+        result["cell_diag"] = np.empty(_abi.SPLASH_NDIAG)
+        cout.cell_diag = _ptr(result["cell_diag"])
+    opts = _abi.SplashOpts()
+    opts.monthly_out = int(bool(monthly_out))
+    ctx.point_run(n_days, year, doy, month, sw_in, tc, pn, lat, elev, slop, asp, soil, au, resolution, opts, cout)
+    result["stats"] = ctx.stats()
+    return result
 
 
 def unSWC_grid(soil_data, uns_depth: float, wn, ctx: Context | None = None) -> dict:

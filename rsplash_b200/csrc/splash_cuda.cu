@@ -9,12 +9,12 @@
 //   k_spin_check/rest one lock-step year pass of the cells that still spin: the check day (which is
 //                     also day 1 of the next pass) with compaction, then days 2..365 of the survivors;
 //                     the list sizes stay on the device, the host never waits for them
-//   k_splash_fused    bulk mode: the run_all day loop of every cell whose spin-up is finished, state in
-//                     registers, constants in shared memory, outputs written with streaming stores
-//                     (daily) or reduced per month in registers (monthly);
-//                     list mode: per-thread state machine (rest of the spin-up, then the day loop)
-//                     for the few cells that outlive the lock-step passes; lanes fetch cells from a
-//                     device-side queue
+//   k_run_bulk        the run_all day loop of every cell whose spin-up is finished, state in registers,
+//                     constants in shared memory, cells in regime-sorted order (k_regime_*), next day's
+//                     forcing prefetched, outputs written with streaming stores (daily) or reduced per
+//                     month in registers (monthly)
+//   k_run_list        per-thread state machine (rest of the spin-up, then the day loop) for the few cells
+//                     that outlive the lock-step passes; lanes fetch cells from a device-side queue
 //   k_pool_*          move those stragglers (constants, state, forcing columns) into a context-wide
 //                     pool so that their tile's buffers can be reused while they finish
 //
@@ -29,6 +29,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -82,6 +86,24 @@ constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
 constexpr int kSpinYear = 365; // R/splash.point.R:141-152: the spin-up year is always 365 days
 
 __constant__ MonthTab c_month_tab;
+
+// -DSPLASH_BOUNDS_CHECK: every index that comes out of a device-side list, queue or pool range is checked before it
+// is used; the first violation is recorded (site id) and fails the call.  compute-sanitizer is not available on the
+// pool's boxes, this build stands in for it in one GPU test (tests/test_cluster_gpu.py).
+#ifdef SPLASH_BOUNDS_CHECK
+__device__ unsigned long long g_bounds_err = 0;
+#define SPLASH_CHECK(cond, site)                                          \
+    do {                                                                  \
+        if (!(cond)) {                                                    \
+            atomicCAS(&g_bounds_err, 0ULL, (unsigned long long)(site));   \
+            return;                                                       \
+        }                                                                 \
+    } while (0)
+#else
+#define SPLASH_CHECK(cond, site) \
+    do {                         \
+    } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // accessors for the per-cell constant matrix
@@ -160,18 +182,19 @@ __global__ void __launch_bounds__(128) k_cell_setup(SetupParams p) {
 template <typename FT>
 __global__ void __launch_bounds__(256) k_snow_threshold(const FT* __restrict__ tc, int64_t fpitch, int n_days,
                                                         int n_cells, double* cc, int64_t cpitch, double* diag,
-                                                        int64_t dpitch) {
+                                                        int64_t dpitch, int* frost) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     StridedCC ccg{cc + c, cpitch};
     // Tt <- max(tc[p_snow >= 0.5]); an NA probability makes the result NA, an empty set gives -Inf
     double Tt = -INFINITY;
     bool any_na = false;
-    int n_snow = 0;
+    int n_snow = 0, n_frost = 0;
     const FT* col = tc + c;
 #pragma unroll 4
     for (int d = 0; d < n_days; ++d) {
         const double t = ld_stream(col + (int64_t)d * fpitch);
+        n_frost += (t < 0.0) ? 1 : 0;
         const int snowy = snow_class(ccg, t);
         if (snowy < 0) {
             any_na = true;
@@ -182,6 +205,7 @@ __global__ void __launch_bounds__(256) k_snow_threshold(const FT* __restrict__ t
     }
     if (any_na) Tt = nan("");
     ccg(C_TT) = Tt;
+    if (frost) frost[c] = n_frost;
     if (diag) {
         diag[SPLASH_DIAG_TT * dpitch + c] = Tt;
         diag[SPLASH_DIAG_SNOW_DAYS * dpitch + c] = (double)n_snow;
@@ -201,6 +225,7 @@ __global__ void __launch_bounds__(256) k_snow_threshold(const FT* __restrict__ t
 // ---------------------------------------------------------------------------------------------
 enum : int { ST_ACTIVE = 0, ST_READY_BULK = 1, ST_EXPORTED = 3 };
 constexpr int kMaxRounds = 32;  // upper bound of lock-step year passes per tile
+constexpr int kRegimeKeys = 128; // buckets of the regime sort (k_regime_*)
 
 // Device-resident control block of one tile.  Everything the kernels of a tile need to know about
 // the sizes of its lists lives here, so the host enqueues the whole tile without waiting.
@@ -215,6 +240,8 @@ struct TileCtl {
     unsigned long long hard_n[4], hard_head[4];  // hard_n[s]: cells that exceeded stage s's pass budget; cursor of the stage that reads them
     unsigned long long tail_head, tail_end;  // leftovers that did not fit the pool: finished in the tile
     unsigned long long max_chain;            // most year passes executed by one thread of a list-mode launch
+    unsigned long long n_ready;              // cells in the regime-sorted order of the bulk launch
+    unsigned long long regime[kRegimeKeys];  // regime sort: bucket counts, then bucket cursors
 };
 
 struct Work {
@@ -224,6 +251,8 @@ struct Work {
     int* passes;
     int* snap_pass;
     int* status;
+    int* frost;          // days with tc < 0 (k_snow_threshold): a key of the regime sort (null in the pool's view)
+    unsigned char* key;  // regime-sort bucket of the cell
     int64_t pitch;
 };
 
@@ -242,9 +271,11 @@ struct RunParams {
     int n_cells;               // cells of the tile
     Work w;
     int* lists[2];             // ping-pong spin lists of the tile: list r lives in lists[r & 1] (list 0 = identity)
+    const int* order;          // k_run_bulk: regime-sorted cell order (ctl->n_ready entries); null = identity
+    int* order_w;              // ... as written by k_regime_scatter
     int round;                 // k_spin_check / k_spin_rest: lock-step round r
     TileCtl* ctl;              // the tile's control block
-    // list mode of k_splash_fused: lanes fetch i from *q_head while i < *q_end; cell = q_list ? q_list[i] : i
+    // k_run_list: lanes fetch i from *q_head while i < *q_end; cell = q_list ? q_list[i] : i
     unsigned long long* q_head;
     const unsigned long long* q_end;
     const int* q_list;
@@ -351,10 +382,10 @@ template <typename FT>
 __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
     extern __shared__ double s_cc[];
     const int c = blockIdx.x * kUThreads + threadIdx.x;
-    if (c >= p.n_cells) return;  // (an exited thread counts as arrived at the CTA barriers below)
+    const bool live = c < p.n_cells;  // threads past the tile's end idle through the loop: every thread reaches every barrier
     StridedCC cc{s_cc + threadIdx.x, kUThreads};
-    load_cc(p, c, cc);
-    const double RES = cc(C_RES);
+    if (live) load_cc(p, c, cc);
+    const double RES = live ? cc(C_RES) : 0.0;
     CellState st;
     st.wn = RES;  // cold start of SPLASH::spin_up, SPLASH.cpp:1633-1639
     st.snow = st.qin = st.td = st.nd = 0.0;
@@ -363,12 +394,13 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
     double w1 = 0.0;
     for (int it = 0; it < 2 * kSpinYear; ++it) {
         const int d = (it < kSpinYear) ? it : it - kSpinYear;
-        double f_sw, f_tc, f_pn;
-        spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
+        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
+        if (live) spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
         if (kSync >= 1 && (it & kSyncMask) == 0) __syncthreads();
+        if (!live) continue;
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
         if (it < kSpinYear) {
             // first spin_up call: only its pass-0 pet is consumed (R/splash.point.R:148-150)
@@ -389,6 +421,7 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
             w1 = st.wn;
         }
     }
+    if (!live) return;
     store_state(p.w, c, st);
     p.w.w1[c] = w1;
     p.w.passes[c] = 1;
@@ -406,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_spin_check(RunParams p
     const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
     if (i >= p.ctl->cnt[r]) return;
     const int c = (r == 0) ? (int)i : p.lists[r & 1][i];
+    SPLASH_CHECK(c >= 0 && c < p.n_cells, 101);
     StridedCC cc{s_cc + threadIdx.x, kThreads};
     load_cc(p, c, cc);
     const CellState Ek = load_state(p.w, c);
@@ -428,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_spin_check(RunParams p
         store_state(p.w, c, st);  // state after day 1 of pass k+1: k_spin_rest of this round continues from it
         p.w.w1[c] = st.wn;
         const unsigned long long k = atomicAdd(&p.ctl->cnt[r + 1], 1ULL);
+        SPLASH_CHECK(k < (unsigned long long)p.w.pitch, 102);
         p.lists[(r + 1) & 1][k] = c;
     } else {
         // the day-365 state is handed over, not the check day's (R/splash.point.R:164-172): st stays
@@ -443,65 +478,174 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_rest(RunParams p) {
     extern __shared__ double s_cc[];
     const int r = p.round;
     const unsigned long long i = (unsigned long long)blockIdx.x * kUThreads + threadIdx.x;
-    if (i >= p.ctl->cnt[r + 1]) return;  // (an exited thread counts as arrived at the CTA barriers below)
-    const int c = p.lists[(r + 1) & 1][i];
+    const unsigned long long n_list = p.ctl->cnt[r + 1];
+    if ((unsigned long long)blockIdx.x * kUThreads >= n_list) return;  // surplus CTA: all of its threads leave together
+    const bool live = i < n_list;  // the list's last CTA: idle threads still reach every barrier
+    const int c = live ? p.lists[(r + 1) & 1][i] : 0;
+    SPLASH_CHECK(c >= 0 && c < p.n_cells && n_list <= (unsigned long long)p.n_cells, 103);
     StridedCC cc{s_cc + threadIdx.x, kUThreads};
-    load_cc(p, c, cc);
-    CellState st = load_state(p.w, c);
+    CellState st{};
+    if (live) {
+        load_cc(p, c, cc);
+        st = load_state(p.w, c);
+    }
     for (int d = 1; d < kSpinYear; ++d) {
-        double f_sw, f_tc, f_pn;
-        spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
+        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
+        if (live) spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
         if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
+        if (!live) continue;
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
     }
+    if (!live) return;
     store_state(p.w, c, st);  // E_{k+1}: end of the pass
     p.w.passes[c] += 1;
     atomicAdd(&p.ctl->spin_days, (unsigned long long)(kSpinYear - 1));
 }
 
-// ---- K2d: daily integration (run_all), optionally preceded by the rest of a cell's spin-up ---------
-// kBulk:      one thread per cell of the tile, cells whose status is ST_READY_BULK; uniform day loop.
-// otherwise:  list mode.  Each lane fetches a cell from the device-side queue (q_head/q_end/q_list),
-//             finishes its spin-up if it is still ST_ACTIVE (per-thread loop with the reference's
-//             convergence test and exact cycle detection), integrates its days, and fetches the next
-//             one.  Used for the straggler pool and for leftovers that did not fit into it.
+// ---- K2d: daily integration (run_all) ---------------------------------------------------------------
+// Output stage shared by the two day-loop kernels: sm_lim (R/splash.point.R:197-200), then either the daily
+// layers or the monthly reduction in registers (mean(wn, snow, sm_lim) / sum(rest), na.rm = TRUE, :210-211).
+struct MonthAcc {
+    double acc[9];
+    int cnt[3];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+        cnt[0] = cnt[1] = cnt[2] = 0;
+    }
+};
+
+template <bool kMonthly>
+__device__ __forceinline__ void emit_day(const RunParams& p, int c, int d, const DayTab& dt, double wrr, double RES,
+                                         const CellState& st, const DayOut& o, MonthAcc& m) {
+    double sm_lim = (st.wn - RES) / wrr;  // R/splash.point.R:197-200
+    if (sm_lim < 0) sm_lim = 0.0;
+    if (sm_lim > 1) sm_lim = 1.0;
+    const double v[9] = {st.wn, o.ro, o.pet, o.aet, st.snow, o.cond, o.bflow, o.netr, sm_lim};
+    if (kMonthly) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (!isnan(v[k])) m.acc[k] += v[k];
+        if (!isnan(v[0])) ++m.cnt[0];
+        if (!isnan(v[4])) ++m.cnt[1];
+        if (!isnan(v[8])) ++m.cnt[2];
+        const bool last = (d + 1 == p.n_days) || (p.dtab[d + 1].group != dt.group);
+        if (last) {
+            const int64_t off = (int64_t)dt.group * p.opitch + c;
+            const double m0 = m.cnt[0] ? m.acc[0] / m.cnt[0] : nan("");
+            const double m4 = m.cnt[1] ? m.acc[4] / m.cnt[1] : nan("");
+            const double m8 = m.cnt[2] ? m.acc[8] / m.cnt[2] : nan("");
+            const double w[9] = {m0, m.acc[1], m.acc[2], m.acc[3], m4, m.acc[5], m.acc[6], m.acc[7], m8};
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (p.out[k]) __stcs(p.out[k] + off, w[k]);
+            m.clear();
+        }
+    } else {
+        const int64_t off = (int64_t)d * p.opitch + c;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (p.out[k]) __stcs(p.out[k] + off, v[k]);
+    }
+}
+
+// Bulk launch: the run_all day loop of every cell of the tile whose spin-up is finished, one thread per cell,
+// uniform day loop (every live thread of the CTA runs days 0..n_days-1; the CTA meets at a barrier per day).
+// Thread i integrates cell p.order[i] (i < ctl->n_ready): the tile's cells regime-sorted by k_regime_*, so that
+// the cells of a warp take the same branches of the day step more often (flat / sloped, deep / shallow soil,
+// frost and snow frequency, aridity); without an order, cell i.  The next day's forcing is loaded before the
+// current day is computed, so that the (scattered, L2-resident) loads are off the dependent path.
+template <typename FT, bool kMonthly>
+__global__ void __launch_bounds__(kUBound, kUBlocks) k_run_bulk(RunParams p) {
+    extern __shared__ double s_cc[];
+    StridedCC cc{s_cc + threadIdx.x, kUThreads};
+    const long long i0 = (long long)blockIdx.x * kUThreads;
+    const long long n_run = p.order ? (long long)p.ctl->n_ready : (long long)p.n_cells;
+    if (i0 >= n_run) return;  // surplus CTA: all of its threads leave together
+    const long long i = i0 + threadIdx.x;
+    int c = 0;
+    bool live = i < n_run;
+    if (live) {
+        c = p.order ? p.order[i] : (int)i;
+        SPLASH_CHECK(c >= 0 && c < p.n_cells && n_run <= (long long)p.n_cells, 104);
+        live = p.w.status[c] == ST_READY_BULK;
+    }
+    const FT* sw_col = (const FT*)p.sw + c;
+    const FT* tc_col = (const FT*)p.tc + c;
+    const FT* pn_col = (const FT*)p.pn + c;
+    CellState st{};
+    double RES = 0.0, wrr = 1.0;
+    if (live) {
+        load_cc(p, c, cc);
+        RES = cc(C_RES);
+        wrr = cc(C_WRR);
+        st = load_state(p.w, c);
+    }
+    int n_snowfall = 0;
+    MonthAcc macc;
+    macc.clear();
+    double n_sw = 0.0, n_tc = 0.0, n_pn = 0.0;  // forcing of the next day
+    if (live && p.n_days > 0) {
+        n_sw = ld_stream(sw_col);
+        n_tc = ld_stream(tc_col);
+        n_pn = ld_stream(pn_col);
+    }
+    for (int d = 0; d < p.n_days; ++d) {
+        const double f_sw = n_sw, f_tc = n_tc, f_pn = n_pn;
+        if (live && d + 1 < p.n_days) {
+            const int64_t off = (int64_t)(d + 1) * p.fpitch;
+            n_sw = ld_stream(sw_col + off);
+            n_tc = ld_stream(tc_col + (int64_t)(d + 1) * p.tpitch);
+            n_pn = ld_stream(pn_col + off);
+        }
+        const DayTab dt = p.dtab[d];
+        if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
+        if (!live) continue;
+        DayOut o;
+        double rain, snowfall;
+        splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
+        if (snowfall > 0.0) ++n_snowfall;
+        emit_day<kMonthly>(p, c, d, dt, wrr, RES, st, o, macc);
+    }
+    if (!live) return;
+    store_state(p.w, c, st);
+    if (p.diag) p.diag[SPLASH_DIAG_SNOWFALL_DAYS * p.dpitch + c] = (double)n_snowfall;
+}
+
+// List mode: a per-thread state machine for the few cells that outlive the lock-step rounds (the straggler pool,
+// and leftovers that did not fit into it).  Each lane fetches a cell from the device-side queue
+// (q_head/q_end/q_list), finishes its spin-up if it is still ST_ACTIVE (per-thread loop with the reference's
+// convergence test and exact cycle detection), integrates its days, and fetches the next one.
 enum Phase : int { PH_DONE = -1, PH_SPIN = 1, PH_MAIN = 2 };
 
-template <typename FT, bool kMonthly, bool kBulk>
-__global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBlocks : 16) k_splash_fused(RunParams p) {
-    constexpr int NT = kBulk ? kUThreads : kListThreads;
-    constexpr int kS = kBulk ? kSync : 0;  // bulk launch: every live thread runs days 0..n_days-1 of run_all
+template <typename FT, bool kMonthly>
+__global__ void __launch_bounds__(kListThreads, 16) k_run_list(RunParams p) {
+    constexpr int NT = kListThreads;
     extern __shared__ double s_cc[];
     StridedCC cc{s_cc + threadIdx.x, NT};
-    StridedCC snap{s_cc + (int64_t)NCC_DAY * NT + threadIdx.x, NT};  // 5 private slots after the constants (list mode)
+    StridedCC snap{s_cc + (int64_t)NCC_DAY * NT + threadIdx.x, NT};  // 5 private slots after the constants
     unsigned long long spin_days = 0;
     int max_chain = 0;
 
     for (;;) {
-        int c;
-        if (kBulk) {
-            c = blockIdx.x * NT + threadIdx.x;
-            if (c >= p.n_cells) return;  // (an exited thread counts as arrived at the CTA barriers below)
-        } else {
-            const unsigned long long i = atomicAdd(p.q_head, 1ULL);
-            if (i >= *p.q_end) break;
-            c = p.q_list ? p.q_list[i] : (int)i;
-        }
+        const unsigned long long i = atomicAdd(p.q_head, 1ULL);
+        if (i >= *p.q_end) break;
+        const int c = p.q_list ? p.q_list[i] : (int)i;
+        SPLASH_CHECK(c >= 0 && c < p.n_cells, 105);
         const int status = p.w.status[c];
-        if (kBulk && status != ST_READY_BULK) return;
         load_cc(p, c, cc);
 
         const FT* sw_col = (const FT*)p.sw + c;
         const FT* tc_col = (const FT*)p.tc + c;
         const FT* pn_col = (const FT*)p.pn + c;
 
-        const double RES = cc(C_RES);
+        const double RES = cc(C_RES), wrr = cc(C_WRR);
         CellState st = load_state(p.w, c);
         CellState saved = st;
-        int phase = (!kBulk && status == ST_ACTIVE) ? PH_SPIN : PH_MAIN;
+        int phase = (status == ST_ACTIVE) ? PH_SPIN : PH_MAIN;
         int passes = 0, snap_pass = 0, chain = 0;
         double w1 = 0.0;
         if (phase == PH_SPIN) {
@@ -513,19 +657,15 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
         }
         int d = 0;
         int n_snowfall = 0;
-        // monthly accumulators: sums for all nine layers, counts for the three averaged ones
-        double acc[9];
-        int cnt[3];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-        cnt[0] = cnt[1] = cnt[2] = 0;
+        MonthAcc macc;
+        macc.clear();
         if (phase == PH_MAIN && p.n_days == 0) phase = PH_DONE;
 
         while (phase != PH_DONE) {
             // ---- forcing and day table of (phase, d) ---------------------------------------------------
             DayTab dt;
             double f_sw, f_tc, f_pn;
-            if (kBulk || phase == PH_MAIN) {
+            if (phase == PH_MAIN) {
                 dt = p.dtab[d];
                 const int64_t off = (int64_t)d * p.fpitch;
                 f_sw = ld_stream(sw_col + off);
@@ -538,43 +678,11 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
             }
             DayOut o;
             double rain, snowfall;
-            if (kS >= 1 && (d & kSyncMask) == 0) __syncthreads();
             splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
 
-            if (kBulk || phase == PH_MAIN) {
+            if (phase == PH_MAIN) {
                 if (snowfall > 0.0) ++n_snowfall;
-                double sm_lim = (st.wn - RES) / cc(C_WRR);  // R/splash.point.R:197-200
-                if (sm_lim < 0) sm_lim = 0.0;
-                if (sm_lim > 1) sm_lim = 1.0;
-                const double v[9] = {st.wn, o.ro, o.pet, o.aet, st.snow, o.cond, o.bflow, o.netr, sm_lim};
-                if (kMonthly) {
-                    // mean(wn, snow, sm_lim) / sum(rest), na.rm = TRUE, R/splash.point.R:210-211
-#pragma unroll
-                    for (int k = 0; k < 9; ++k)
-                        if (!isnan(v[k])) acc[k] += v[k];
-                    if (!isnan(v[0])) ++cnt[0];
-                    if (!isnan(v[4])) ++cnt[1];
-                    if (!isnan(v[8])) ++cnt[2];
-                    const bool last = (d + 1 == p.n_days) || (p.dtab[d + 1].group != dt.group);
-                    if (last) {
-                        const int64_t off = (int64_t)dt.group * p.opitch + c;
-                        const double m0 = cnt[0] ? acc[0] / cnt[0] : nan("");
-                        const double m4 = cnt[1] ? acc[4] / cnt[1] : nan("");
-                        const double m8 = cnt[2] ? acc[8] / cnt[2] : nan("");
-                        const double w[9] = {m0, acc[1], acc[2], acc[3], m4, acc[5], acc[6], acc[7], m8};
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            if (p.out[k]) __stcs(p.out[k] + off, w[k]);
-                            acc[k] = 0.0;
-                        }
-                        cnt[0] = cnt[1] = cnt[2] = 0;
-                    }
-                } else {
-                    const int64_t off = (int64_t)d * p.opitch + c;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k)
-                        if (p.out[k]) __stcs(p.out[k] + off, v[k]);
-                }
+                emit_day<kMonthly>(p, c, d, dt, wrr, RES, st, o, macc);
                 if (++d == p.n_days) phase = PH_DONE;
             } else {  // PH_SPIN: the rest of the second spin_up call, SPLASH.cpp:1697-1743
                 ++spin_days;
@@ -600,7 +708,6 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
 
         store_state(p.w, c, st);
         if (p.diag) p.diag[SPLASH_DIAG_SNOWFALL_DAYS * p.dpitch + c] = (double)n_snowfall;
-        if (kBulk) return;
         if (status == ST_ACTIVE) {
             p.w.passes[c] = passes;
             if (p.diag) p.diag[SPLASH_DIAG_SPIN_PASSES * p.dpitch + c] = (double)passes;
@@ -609,6 +716,57 @@ __global__ void __launch_bounds__(kBulk ? kUBound : kListThreads, kBulk ? kUBloc
     }
     if (spin_days) atomicAdd(&p.ctl->spin_days, spin_days);
     if (max_chain) atomicMax(&p.ctl->max_chain, (unsigned long long)max_chain);
+}
+
+// ---- regime sort: a counting sort of the tile's finished cells by a key that predicts which branches of the
+//      day step a cell takes (k_run_bulk runs the cells in this order; results do not depend on it) -------------
+__device__ __forceinline__ int regime_key(const RunParams& p, int c) {
+    const double tan_s = p.cc[(int64_t)C_TAN_S * p.cpitch + c];
+    const double depth = p.cc[(int64_t)C_DEPTH * p.cpitch + c];
+    const double ai = p.cc[(int64_t)C_CELLOUT * p.cpitch + c];  // the aridity index sits in the cellout slot (SURVEY B-3)
+    const double sat = p.cc[(int64_t)C_SAT * p.cpitch + c];
+    if (isnan(sat) || isnan(ai) || isnan(tan_s)) return kRegimeKeys - 1;  // NA cells together
+    const int flat = (tan_s == 0.0) ? 1 : 0;
+    const int deep = (depth >= 2.0) ? 1 : 0;
+    const int nd = p.n_days > 0 ? p.n_days : 1;
+    const int frost = p.w.frost[c];  // days with tc < 0 (viscosity is a cell constant there), k_snow_threshold
+    const int fq = (frost == 0) ? 0 : ((8 * (long long)frost) / nd >= 7 ? 3 : ((2 * (long long)frost >= nd) ? 2 : 1));
+    const int wq = (ai < 0.6) ? 0 : (ai < 1.2) ? 1 : (ai < 2.5) ? 2 : 3;  // humid ... arid
+    return ((flat * 2 + deep) * 4 + fq) * 4 + wq;  // 0..63
+}
+
+__global__ void __launch_bounds__(256) k_regime_count(RunParams p) {
+    __shared__ unsigned int h[kRegimeKeys];
+    for (int k = threadIdx.x; k < kRegimeKeys; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < p.n_cells && p.w.status[c] == ST_READY_BULK) {
+        const int key = regime_key(p, c);
+        p.w.key[c] = (unsigned char)key;
+        atomicAdd(&h[key], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kRegimeKeys; k += blockDim.x)
+        if (h[k]) atomicAdd(&p.ctl->regime[k], (unsigned long long)h[k]);
+}
+
+__global__ void k_regime_scan(TileCtl* ctl) {  // one thread: bucket counts -> bucket cursors
+    unsigned long long run = 0;
+    for (int k = 0; k < kRegimeKeys; ++k) {
+        const unsigned long long n = ctl->regime[k];
+        ctl->regime[k] = run;
+        run += n;
+    }
+    ctl->n_ready = run;
+}
+
+__global__ void __launch_bounds__(256) k_regime_scatter(RunParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < p.n_cells && p.w.status[c] == ST_READY_BULK) {
+        const unsigned long long k = atomicAdd(&p.ctl->regime[p.w.key[c]], 1ULL);
+        SPLASH_CHECK(p.w.key[c] < kRegimeKeys && k < (unsigned long long)p.n_cells, 106);
+        p.order_w[k] = c;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -664,6 +822,7 @@ __global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int
     for (long long e = tid; (part & 1) && e < n; e += nthreads) {
         const int c = list ? list[e] : (int)e;
         const long long j = (long long)base + e;
+        SPLASH_CHECK(c >= 0 && c < p.n_cells && j >= 0 && j < pool.cap, 107);
         for (int k = 0; k < NCC; ++k) pool.cc[(long long)k * pool.cap + j] = p.cc[(int64_t)k * p.cpitch + c];
         for (int k = 0; k < 5; ++k) {
             pool.w.st[(long long)k * pool.cap + j] = p.w.st[(int64_t)k * p.w.pitch + c];
@@ -686,6 +845,7 @@ __global__ void __launch_bounds__(256) k_pool_export(RunParams p, Pool pool, int
         const long long d = q / n, e = q - d * n;
         const int c = list ? list[e] : (int)e;
         const long long dst = d * pool.cap + (long long)base + e;
+        SPLASH_CHECK(c >= 0 && c < p.n_cells && (long long)base + e < pool.cap, 108);
         ((FT*)pool.f[0])[dst] = ((const FT*)src_sw)[d * spitch + c];
         ((FT*)pool.f[1])[dst] = ((const FT*)p.tc)[d * p.tpitch + c];
         ((FT*)pool.f[2])[dst] = ((const FT*)src_pn)[d * spitch + c];
@@ -704,6 +864,7 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n * kSpinYear; q += nthreads) {
         const int d = (int)(q / n);
         const int j = (int)(base + (q - (long long)d * n));
+        SPLASH_CHECK(j >= 0 && j < pool.cap, 109);
         StridedCC cc{p.cc + j, p.cpitch};
         double f_sw, f_tc, f_pn;
         spin_forcing<FT>(p, j, d, f_sw, f_tc, f_pn);
@@ -752,6 +913,7 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
             if (i >= p.ctl->hard_n[stage - 1]) break;
             c = pool.hard[(stage - 1) & 1][p.ctl->pool_base + i];
         }
+        SPLASH_CHECK(c >= 0 && c < pool.cap && (unsigned long long)c >= p.ctl->pool_base && (unsigned long long)c < p.ctl->pool_end, 110);
         load_cc(p, c, cc);
         CellState st = load_state(p.w, c);
         CellState saved = st;
@@ -804,6 +966,7 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
 #pragma unroll
             for (int k = 0; k < 5; ++k) p.w.snap[(int64_t)k * p.w.pitch + c] = snap(k);
             const unsigned long long k2 = atomicAdd(&p.ctl->hard_n[stage], 1ULL);
+            SPLASH_CHECK(p.ctl->pool_base + k2 < p.ctl->pool_end, 111);
             pool.hard[stage & 1][p.ctl->pool_base + k2] = c;
             continue;
         }
@@ -818,8 +981,13 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
 }
 
 // device-resident outputs: write the pool's results into the caller's arrays
-__global__ void k_pool_scatter(Pool pool, long long n, long long n_out, double* const* out9, long long ostride,
+struct Out9 {
+    double* p[9];
+};
+
+__global__ void k_pool_scatter(Pool pool, long long n, long long n_out, Out9 o9, long long ostride,
                                double* state_final, double* cell_diag, long long nc) {
+    double* const* out9 = o9.p;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (int k = 0; k < 9; ++k) {
@@ -834,6 +1002,7 @@ __global__ void k_pool_scatter(Pool pool, long long n, long long n_out, double* 
         if (state_final) {
             for (int k = 0; k < 5; ++k) state_final[(long long)k * nc + c] = pool.w.st[(long long)k * pool.cap + j];
             state_final[5LL * nc + c] = pool.cc[(long long)C_CELLOUT * pool.cap + j];
+            state_final[6LL * nc + c] = pool.cc[(long long)C_TT * pool.cap + j];
         }
         if (cell_diag) {
             cell_diag[(long long)SPLASH_DIAG_SPIN_PASSES * nc + c] = pool.diag[(long long)SPLASH_DIAG_SPIN_PASSES * pool.cap + j];
@@ -952,6 +1121,8 @@ __global__ void k_tile_begin(TileCtl* ctl, int n_cells) {  // (the control block
 
 // resume: the carried aridity index (row 5 of state_init, parked in w.w1) goes where the interrupted run
 // had it, soil_info[12] == `cellout` (R/splash.point.R:150, SURVEY B-3)
+// ... and the carried snowfall threshold (row 6, parked in w.snap) replaces the one k_snow_threshold took from this
+// segment of the series alone: Tt is a reduction over the WHOLE series (R/splash.point.R:120-122)
 __global__ void k_init_resume(Work w, double* cc, int64_t cpitch, double* diag, int64_t dpitch, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -960,7 +1131,12 @@ __global__ void k_init_resume(Work w, double* cc, int64_t cpitch, double* diag, 
     StridedCC ccg{cc + c, cpitch};
     const double AI = w.w1[c];
     lateral_consts(ccg, AI);
-    if (diag) diag[SPLASH_DIAG_AI * dpitch + c] = AI;
+    const double Tt = w.snap[c];
+    ccg(C_TT) = Tt;
+    if (diag) {
+        diag[SPLASH_DIAG_AI * dpitch + c] = AI;
+        diag[SPLASH_DIAG_TT * dpitch + c] = Tt;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1207,11 +1383,14 @@ constexpr int kPoolStage2Passes = 128;  // ... and of the second; the third runs
 static_assert(kRounds <= kMaxRounds, "kRounds");
 constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
 
+constexpr int kWorkInts = 8;  // int arrays of a work set: passes, snap_pass, status, 2 spin lists, frost days, bulk order, sort keys
 struct WorkSet {  // per-tile work arrays (per slot when the inputs stream from the host)
     DevBuf cc, work_d, work_i, diag;
 };
 
 }  // namespace
+
+struct splash_cluster;
 
 struct splash_ctx {
     int device = 0;
@@ -1236,6 +1415,10 @@ struct splash_ctx {
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
     int64_t pool_cap = 0;                 // SPLASH_POOL_CAP: force the pool capacity (tests of the overflow path)
     int spin_ahead = 1;                   // SPLASH_SPIN_AHEAD=0: host-fed calls upload tile by tile (no spin-up data first)
+    int regime_sort = 1;                  // SPLASH_REGIME_SORT=0: the bulk launch takes the cells in grid order
+    double mem_share = 1.0;               // share of the device's memory this context may plan with (lanes of a cluster)
+    // a context over several GPUs (splash_ctx_create_multi): the work goes to the cluster's lanes
+    splash_cluster* multi = nullptr;
 };
 
 namespace {
@@ -1275,6 +1458,13 @@ int ensure(splash_ctx* ctx, DevBuf& b, size_t bytes) {
     return SPLASH_OK;
 }
 
+struct TmpDev {  // a temporary device buffer that is released on every return path
+    void* p = nullptr;
+    ~TmpDev() {
+        if (p) cudaFree(p);
+    }
+};
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 inline unsigned ugrid_for(int64_t n) { return (unsigned)((n + kUThreads - 1) / kUThreads); }
@@ -1289,10 +1479,10 @@ cudaError_t prepare_kernels() {
     if ((e = cudaFuncSetAttribute(k_spin_first<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
     if ((e = cudaFuncSetAttribute(k_spin_check<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpin))) return e;
     if ((e = cudaFuncSetAttribute(k_spin_rest<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
-    if ((e = cudaFuncSetAttribute(k_splash_fused<FT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_list<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_list<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
     return cudaSuccess;
 }
@@ -1302,23 +1492,19 @@ template <typename FT>
 void launch_bulk(const RunParams& rp, bool monthly, cudaStream_t s) {
     if (rp.n_cells <= 0) return;
     if (monthly)
-        k_splash_fused<FT, true, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
+        k_run_bulk<FT, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
     else
-        k_splash_fused<FT, false, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
+        k_run_bulk<FT, false><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
 }
 
 // list-mode launch: `warps` one-warp CTAs whose lanes fetch cells from the queue in rp
 template <typename FT>
 void launch_list(const RunParams& rp, bool monthly, int warps, cudaStream_t s) {
     if (monthly)
-        k_splash_fused<FT, true, false><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
+        k_run_list<FT, true><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
     else
-        k_splash_fused<FT, false, false><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
+        k_run_list<FT, false><<<(unsigned)warps, kListThreads, kSmemList, s>>>(rp);
 }
-
-struct Out9 {
-    double* p[9];
-};
 
 }  // namespace
 
@@ -1329,6 +1515,8 @@ extern "C" {
 
 int splash_abi_version(void) { return SPLASH_ABI_VERSION; }
 
+static splash_ctx* first_lane(splash_ctx* ctx);
+
 static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& prop);
 
 int splash_ctx_create(int device, splash_ctx** out_ctx) {
@@ -1337,10 +1525,9 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     *out_ctx = nullptr;
     // The call keeps ~25 streams busy (tiles, straggler pool, copies).  With the default of 8 hardware
     // work queues several streams share one, and a tile's next kernel then waits behind another
-    // stream's seconds-long pool kernel (measured: tiles 4..7 started 2.6 s late).  Only effective if
-    // CUDA is not initialised in this process yet; hosts that initialise CUDA first (PyTorch) must
-    // export the variable themselves (rsplash_b200/__init__.py does).
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // stream's seconds-long pool kernel (measured: tiles 4..7 started 2.6 s late).  The host process
+    // exports CUDA_DEVICE_MAX_CONNECTIONS=32 before it initialises CUDA (include/splash_cuda.h,
+    // INTEGRATION.md); the library does not touch the environment.
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)
@@ -1351,7 +1538,7 @@ int splash_ctx_create(int device, splash_ctx** out_ctx) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return fail(nullptr, SPLASH_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-    if (prop.major < 10)
+    if (prop.major != 10 || prop.minor != 0)  // the library embeds sm_100a SASS only (no PTX to JIT for other parts)
         return fail(nullptr, SPLASH_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     ctx = new splash_ctx();
@@ -1385,6 +1572,7 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     if (const char* v = getenv("SPLASH_ROUNDS_RT")) ctx->n_rounds = std::max(0, std::min(kRounds, atoi(v)));
     if (const char* v = getenv("SPLASH_POOL_CAP")) ctx->pool_cap = std::max<int64_t>(32, atoll(v));
     if (const char* v = getenv("SPLASH_SPIN_AHEAD")) ctx->spin_ahead = atoi(v) != 0;
+    if (const char* v = getenv("SPLASH_REGIME_SORT")) ctx->regime_sort = atoi(v) != 0;
     CU(cudaSetDevice(device));
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1402,6 +1590,11 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
 
 void splash_ctx_destroy(splash_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->multi) {
+        splash_cluster_destroy(ctx->multi);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     auto fr = [](DevBuf& b) {
@@ -1451,22 +1644,32 @@ int splash_last_stats(const splash_ctx* ctx, splash_stats* out) {
 }
 
 int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, double* y) {
+    if (ctx && ctx->multi) {  // single-GPU work: the context's first lane does it
+        splash_ctx* lane = first_lane(ctx);
+        const int rc = splash_debug_math(lane, op, n, x, y);
+        ctx->err = lane->err;
+        return rc;
+    }
     if (!ctx || !x || !y || n < 0 || op < 0 || op > 3) return SPLASH_ERR_BAD_ARG;
     if (n == 0) return SPLASH_OK;
     CU(cudaSetDevice(ctx->device));
-    double *dx = nullptr, *dy = nullptr;
-    CU(cudaMalloc(&dx, (size_t)n * 8));
-    CU(cudaMalloc(&dy, (size_t)n * 8));
-    CU(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
-    k_debug_math<<<(unsigned)((n + 255) / 256), 256>>>(op, n, dx, dy);
+    TmpDev dx, dy;  // freed on every return path
+    CU(cudaMalloc(&dx.p, (size_t)n * 8));
+    CU(cudaMalloc(&dy.p, (size_t)n * 8));
+    CU(cudaMemcpy(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    k_debug_math<<<(unsigned)((n + 255) / 256), 256>>>(op, n, (const double*)dx.p, (double*)dy.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    CU(cudaFree(dx));
-    CU(cudaFree(dy));
+    CU(cudaMemcpy(y, dy.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return SPLASH_OK;
 }
 
 int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_unswc_out* out) {
+    if (ctx && ctx->multi) {  // single-GPU work: the context's first lane does it
+        splash_ctx* lane = first_lane(ctx);
+        const int rc = splash_unswc_grid_run(lane, in, out);
+        ctx->err = lane->err;
+        return rc;
+    }
     if (!ctx) return SPLASH_ERR_BAD_ARG;
     ctx->err.clear();
     if (!in || !out) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_unswc_grid_run: NULL in/out");
@@ -1504,10 +1707,11 @@ int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_uns
     int n_o = 0;
     for (auto q : optr) n_o += q ? 1 : 0;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nl, ((int64_t)1 << 30) / std::max<int64_t>(1, nc * 8 * (1 + n_o))));
-    double *d_soil = nullptr, *d_wn = nullptr, *d_out = nullptr;
-    CU(cudaMalloc(&d_soil, (size_t)6 * nc * 8));
-    CU(cudaMalloc(&d_wn, (size_t)chunk * nc * 8));
-    if (n_o) CU(cudaMalloc(&d_out, (size_t)n_o * chunk * nc * 8));
+    TmpDev t_soil, t_wn, t_out;  // freed on every return path
+    CU(cudaMalloc(&t_soil.p, (size_t)6 * nc * 8));
+    CU(cudaMalloc(&t_wn.p, (size_t)chunk * nc * 8));
+    if (n_o) CU(cudaMalloc(&t_out.p, (size_t)n_o * chunk * nc * 8));
+    double *d_soil = (double*)t_soil.p, *d_wn = (double*)t_wn.p, *d_out = (double*)t_out.p;
     CU(cudaMemcpyAsync(d_soil, in->soil, (size_t)6 * nc * 8, cudaMemcpyHostToDevice, S));
     p.soil = d_soil;
     p.soil_pitch = nc;
@@ -1529,14 +1733,17 @@ int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_uns
                                              cudaMemcpyDeviceToHost, S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
         if (cudaStreamSynchronize(S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
     }
-    cudaFree(d_soil);
-    cudaFree(d_wn);
-    if (d_out) cudaFree(d_out);
     if (rc != SPLASH_OK) return fail(ctx, rc, "splash_unswc_grid_run: %s", cudaGetErrorString(cudaGetLastError()));
     return SPLASH_OK;
 }
 
 int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* daily_out) {
+    if (ctx && ctx->multi) {  // single-GPU work: the context's first lane does it
+        splash_ctx* lane = first_lane(ctx);
+        const int rc = splash_month2day_linear(lane, in, daily_out);
+        ctx->err = lane->err;
+        return rc;
+    }
     if (!ctx) return SPLASH_ERR_BAD_ARG;
     ctx->err.clear();
     if (!in) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_month2day_linear: NULL in");
@@ -1708,6 +1915,7 @@ struct GridJob {
     splash_grid_out* out;
     splash_opts opts;
     int64_t nc, nd, n_out, istride, ostride;
+    int64_t apitch, xpitch, spitch;  // layer pitches of soil/au, of state_final/cell_diag, of state_init
     bool in_dev, out_dev, monthly;
     int max_spin;
     double spin_tol;
@@ -1751,7 +1959,8 @@ struct GridJob {
             held += ctx->cellin[i].cap + ctx->outs[i].cap;
         }
         for (auto& w : ctx->work) held += w.cc.cap + w.work_d.cap + w.work_i.cap + w.diag.cap;
-        double budget = 0.80 * (double)(free_b + held);
+        // (a lane of a cluster shares its device with the other lanes)
+        double budget = 0.80 * (double)(free_b + held) * ctx->mem_share;
 
         // ---- straggler pool: a slice of the budget, ~4 % of the cells -----------------------------------
         const double per_entry = 3.0 * (double)std::max<int64_t>(nd, 1) * fsz + (double)(NCC + 11 + SPLASH_NDIAG + 1) * 8.0 + 12.0 +
@@ -1792,6 +2001,8 @@ struct GridJob {
             pool.w.passes = wi;
             pool.w.snap_pass = wi + cap;
             pool.w.status = wi + 2 * cap;
+            pool.w.frost = nullptr;
+            pool.w.key = nullptr;
             pool.w.pitch = cap;
             int li = 0;
             for (int k = 0; k < 9; ++k)
@@ -1807,7 +2018,7 @@ struct GridJob {
         }
 
         // ---- host-fed calls: spin-up data of all tiles ahead of the bulk of the forcing, if it fits --------
-        const double work_cell = (double)(NCC + 11 + SPLASH_NDIAG) * 8.0 + 5 * 4.0;
+        const double work_cell = (double)(NCC + 11 + SPLASH_NDIAG) * 8.0 + kWorkInts * 4.0;
         nd1 = std::min<int64_t>(nd, kSpinYear);
         ncp = round_up(nc, 32);
         const double ahead_bytes = (double)ncp * ((double)(nd + 2 * nd1) * fsz + 14 * 8.0);
@@ -1852,7 +2063,7 @@ struct GridJob {
             WorkSet& ws = ctx->work[(size_t)w];
             if (int rc = ensure(ctx, ws.cc, (size_t)NCC * pitch * 8)) return rc;
             if (int rc = ensure(ctx, ws.work_d, (size_t)11 * pitch * 8)) return rc;
-            if (int rc = ensure(ctx, ws.work_i, (size_t)5 * pitch * 4)) return rc;
+            if (int rc = ensure(ctx, ws.work_i, (size_t)kWorkInts * pitch * 4)) return rc;
             if (int rc = ensure(ctx, ws.diag, (size_t)SPLASH_NDIAG * pitch * 8)) return rc;
         }
         const int n_slots = (int)std::min<int64_t>(kSlots, n_tiles);
@@ -1927,8 +2138,8 @@ struct GridJob {
         const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
         for (int k = 0; k < 5; ++k)
             CU(cudaMemcpyAsync(ci + (size_t)k * ncp, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
-        CU(cudaMemcpy2DAsync(ci + (size_t)5 * ncp, (size_t)ncp * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6, cudaMemcpyHostToDevice, H));
-        CU(cudaMemcpy2DAsync(ci + (size_t)11 * ncp, (size_t)ncp * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8, (size_t)in->au_layers,
+        CU(cudaMemcpy2DAsync(ci + (size_t)5 * ncp, (size_t)ncp * 8, in->soil + c0, (size_t)apitch * 8, (size_t)nct * 8, 6, cudaMemcpyHostToDevice, H));
+        CU(cudaMemcpy2DAsync(ci + (size_t)11 * ncp, (size_t)ncp * 8, in->au + c0, (size_t)apitch * 8, (size_t)nct * 8, (size_t)in->au_layers,
                              cudaMemcpyHostToDevice, H));
         ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
         CU(cudaEventRecord(ev[(size_t)t].h2da, H));
@@ -1959,9 +2170,9 @@ struct GridJob {
                 const double* vec[5] = {in->lat, in->elev, in->slop, in->asp, in->resolution};
                 for (int k = 0; k < 5; ++k)
                     CU(cudaMemcpyAsync(ci + (size_t)k * pitch, vec[k] + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, H));
-                CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)nc * 8, (size_t)nct * 8, 6,
+                CU(cudaMemcpy2DAsync(ci + (size_t)5 * pitch, (size_t)pitch * 8, in->soil + c0, (size_t)apitch * 8, (size_t)nct * 8, 6,
                                      cudaMemcpyHostToDevice, H));
-                CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)nc * 8, (size_t)nct * 8,
+                CU(cudaMemcpy2DAsync(ci + (size_t)11 * pitch, (size_t)pitch * 8, in->au + c0, (size_t)apitch * 8, (size_t)nct * 8,
                                      (size_t)in->au_layers, cudaMemcpyHostToDevice, H));
                 ctx->stats.h2d_bytes += (int64_t)nct * 8 * (5 + 6 + in->au_layers);
             }
@@ -1992,9 +2203,9 @@ struct GridJob {
             sp.asp = in->asp + c0;
             sp.resolution = in->resolution + c0;
             sp.soil = in->soil + c0;
-            sp.soil_pitch = nc;
+            sp.soil_pitch = apitch;
             sp.au = in->au + c0;
-            sp.au_pitch = nc;
+            sp.au_pitch = apitch;
         } else {
             rp.sw = ctx->forcing[s][0].p;
             rp.pn = ctx->forcing[s][2].p;
@@ -2049,9 +2260,13 @@ struct GridJob {
         rp.w.passes = wi;
         rp.w.snap_pass = wi + pitch;
         rp.w.status = wi + 2 * pitch;
+        rp.w.frost = wi + 5 * pitch;
+        rp.w.key = (unsigned char*)(wi + 7 * pitch);
         rp.w.pitch = pitch;
         rp.lists[0] = wi + 3 * pitch;
         rp.lists[1] = wi + 4 * pitch;
+        rp.order = nullptr;
+        rp.order_w = wi + 6 * pitch;
         rp.ctl = ctl(t);
         int li = 0;
         for (int k = 0; k < 9; ++k) {
@@ -2086,15 +2301,16 @@ struct GridJob {
         k_cell_setup<<<(unsigned)((nct + 127) / 128), 128, 0, R>>>(sps[(size_t)t]);
         CU(cudaGetLastError());
         k_snow_threshold<FT><<<(unsigned)((nct + 255) / 256), 256, 0, R>>>((const FT*)rp.tc, rp.tpitch, rp.n_days, (int)nct, rp.cc,
-                                                                            rp.cpitch, rp.diag, rp.dpitch);
+                                                                            rp.cpitch, rp.diag, rp.dpitch, rp.w.frost);
         CU(cudaGetLastError());
         launches += 3;
         CU(cudaEventRecord(e.kf0, R));
         if (opts.skip_spinup) {
             // resume: run_all starts from the caller's state (SPLASH.cpp:1833-1835 wn_last ... nds_last)
-            CU(cudaMemcpy2DAsync(rp.w.st, (size_t)pitch * 8, opts.state_init + c0, (size_t)nc * 8, (size_t)nct * 8, 5,
+            CU(cudaMemcpy2DAsync(rp.w.st, (size_t)pitch * 8, opts.state_init + c0, (size_t)spitch * 8, (size_t)nct * 8, 5,
                                  cudaMemcpyHostToDevice, R));
-            CU(cudaMemcpyAsync(rp.w.w1, opts.state_init + 5 * nc + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, R));
+            CU(cudaMemcpyAsync(rp.w.w1, opts.state_init + 5 * spitch + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, R));
+            CU(cudaMemcpyAsync(rp.w.snap, opts.state_init + 6 * spitch + c0, (size_t)nct * 8, cudaMemcpyHostToDevice, R));
             k_init_resume<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp.w, rp.cc, rp.cpitch, rp.diag, rp.dpitch, (int)nct);
             CU(cudaGetLastError());
             ++launches;
@@ -2197,6 +2413,16 @@ struct GridJob {
             CU(cudaGetLastError());
             ++launches;
         }
+        if (ctx->regime_sort && nd > 0) {
+            // the finished cells in regime order (exported stragglers and, after a resume, nothing are left out)
+            CU(cudaMemsetAsync(&rp.ctl->n_ready, 0, sizeof(unsigned long long) * (1 + kRegimeKeys), R));
+            k_regime_count<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp);
+            k_regime_scan<<<1, 1, 0, R>>>(rp.ctl);
+            k_regime_scatter<<<(unsigned)((nct + 255) / 256), 256, 0, R>>>(rp);
+            CU(cudaGetLastError());
+            launches += 3;
+            rp.order = rp.order_w;
+        }
         CU(cudaEventRecord(e.kb0, R));
         launch_bulk<FT>(rp, monthly, R);
         CU(cudaGetLastError());
@@ -2218,12 +2444,13 @@ struct GridJob {
             }
         }
         if (out->state_final) {
-            CU(cudaMemcpy2DAsync(out->state_final + c0, (size_t)nc * 8, rp.w.st, (size_t)pitch * 8, (size_t)nct * 8, 5, okind, D));
-            CU(cudaMemcpyAsync(out->state_final + 5 * nc + c0, rp.cc + (size_t)C_CELLOUT * pitch, (size_t)nct * 8, okind, D));
+            CU(cudaMemcpy2DAsync(out->state_final + c0, (size_t)xpitch * 8, rp.w.st, (size_t)pitch * 8, (size_t)nct * 8, 5, okind, D));
+            CU(cudaMemcpyAsync(out->state_final + 5 * xpitch + c0, rp.cc + (size_t)C_CELLOUT * pitch, (size_t)nct * 8, okind, D));
+            CU(cudaMemcpyAsync(out->state_final + 6 * xpitch + c0, rp.cc + (size_t)C_TT * pitch, (size_t)nct * 8, okind, D));
             if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * SPLASH_NSTATE * 8;
         }
         if (out->cell_diag) {
-            CU(cudaMemcpy2DAsync(out->cell_diag + c0, (size_t)nc * 8, rp.diag, (size_t)pitch * 8, (size_t)nct * 8, SPLASH_NDIAG, okind, D));
+            CU(cudaMemcpy2DAsync(out->cell_diag + c0, (size_t)xpitch * 8, rp.diag, (size_t)pitch * 8, (size_t)nct * 8, SPLASH_NDIAG, okind, D));
             if (!out_dev) ctx->stats.d2h_bytes += (int64_t)nct * SPLASH_NDIAG * 8;
         }
         CU(cudaEventRecord(e.d2h1, D));
@@ -2236,16 +2463,12 @@ struct GridJob {
         if (out_dev) {
             Out9 o9;
             for (int k = 0; k < 9; ++k) o9.p[k] = out_ptr[k];
-            DevBuf tmp;  // nine pointers
-            if (int rc = ensure(ctx, tmp, sizeof(Out9))) return rc;
-            CU(cudaMemcpy(tmp.p, &o9, sizeof(Out9), cudaMemcpyHostToDevice));
-            k_pool_scatter<<<(unsigned)(ctx->sm_count * 2), 256, 0, ctx->s_d2h>>>(pool, (long long)n_pool, (long long)n_out,
-                                                                                 (double* const*)tmp.p, (long long)ostride,
-                                                                                 out->state_final, out->cell_diag, (long long)nc);
+            k_pool_scatter<<<(unsigned)(ctx->sm_count * 2), 256, 0, ctx->s_d2h>>>(pool, (long long)n_pool, (long long)n_out, o9,
+                                                                                 (long long)ostride, out->state_final, out->cell_diag,
+                                                                                 (long long)xpitch);
             CU(cudaGetLastError());
             ++launches;
             CU(cudaStreamSynchronize(ctx->s_d2h));
-            CU(cudaFree(tmp.p));
             return SPLASH_OK;
         }
         std::vector<long long> cell((size_t)n_pool);
@@ -2276,16 +2499,18 @@ struct GridJob {
         if (out->state_final) {
             CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.w.st, (size_t)pool.cap * 8, (size_t)n_pool * 8, 5, cudaMemcpyDeviceToHost));
             for (int k = 0; k < 5; ++k)
-                for (int64_t j = 0; j < n_pool; ++j) out->state_final[(int64_t)k * nc + cell[(size_t)j]] = buf[(size_t)(k * n_pool + j)];
+                for (int64_t j = 0; j < n_pool; ++j) out->state_final[(int64_t)k * xpitch + cell[(size_t)j]] = buf[(size_t)(k * n_pool + j)];
             CU(cudaMemcpy(buf.data(), pool.cc + (size_t)C_CELLOUT * pool.cap, (size_t)n_pool * 8, cudaMemcpyDeviceToHost));
-            for (int64_t j = 0; j < n_pool; ++j) out->state_final[5 * nc + cell[(size_t)j]] = buf[(size_t)j];
+            for (int64_t j = 0; j < n_pool; ++j) out->state_final[5 * xpitch + cell[(size_t)j]] = buf[(size_t)j];
+            CU(cudaMemcpy(buf.data(), pool.cc + (size_t)C_TT * pool.cap, (size_t)n_pool * 8, cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < n_pool; ++j) out->state_final[6 * xpitch + cell[(size_t)j]] = buf[(size_t)j];
         }
         if (out->cell_diag) {
             CU(cudaMemcpy2D(buf.data(), (size_t)n_pool * 8, pool.diag, (size_t)pool.cap * 8, (size_t)n_pool * 8, SPLASH_NDIAG,
                             cudaMemcpyDeviceToHost));
             const int rows[2] = {SPLASH_DIAG_SPIN_PASSES, SPLASH_DIAG_SNOWFALL_DAYS};
             for (int r : rows)
-                for (int64_t j = 0; j < n_pool; ++j) out->cell_diag[(int64_t)r * nc + cell[(size_t)j]] = buf[(size_t)(r * n_pool + j)];
+                for (int64_t j = 0; j < n_pool; ++j) out->cell_diag[(int64_t)r * xpitch + cell[(size_t)j]] = buf[(size_t)(r * n_pool + j)];
         }
         return SPLASH_OK;
     }
@@ -2339,6 +2564,13 @@ struct GridJob {
         CU(cudaEventRecord(ev_end, ctx->s_d2h));
         CU(cudaEventSynchronize(ev_end));
 
+#ifdef SPLASH_BOUNDS_CHECK
+        {
+            unsigned long long site = 0;
+            CU(cudaMemcpyFromSymbol(&site, g_bounds_err, sizeof(site)));
+            if (site) return fail(ctx, SPLASH_ERR_CUDA, "bounds check failed in a kernel (site %llu)", site);
+        }
+#endif
         // ---- accounting --------------------------------------------------------------------------------------
         std::vector<TileCtl> h_ctl((size_t)n_tiles);
         CU(cudaMemcpy(h_ctl.data(), ctx->ctl.p, sizeof(TileCtl) * (size_t)n_tiles, cudaMemcpyDeviceToHost));
@@ -2399,8 +2631,11 @@ struct GridJob {
 
 extern "C" {
 
+static int multi_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts* opts_in, splash_grid_out* out);
+
 int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts* opts_in, splash_grid_out* out) {
     if (!ctx) return SPLASH_ERR_BAD_ARG;
+    if (ctx->multi) return multi_grid_run(ctx, in, opts_in, out);
     const auto t_begin = std::chrono::steady_clock::now();
     ctx->err.clear();
     ctx->stats = splash_stats{};
@@ -2419,10 +2654,14 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
     const int64_t istride = in->cell_stride ? in->cell_stride : nc;
     const int64_t ostride = out->cell_stride ? out->cell_stride : nc;
     if (istride < nc || ostride < nc) return fail(ctx, SPLASH_ERR_BAD_ARG, "cell_stride smaller than n_cells");
+    const int64_t apitch = in->attr_stride ? in->attr_stride : nc;
+    const int64_t xpitch = out->aux_stride ? out->aux_stride : nc;
+    const int64_t spitch = opts.state_stride ? opts.state_stride : nc;
+    if (apitch < nc || xpitch < nc || spitch < nc) return fail(ctx, SPLASH_ERR_BAD_ARG, "attr_stride/aux_stride/state_stride smaller than n_cells");
     if (nc > 0 && (!in->lat || !in->elev || !in->slop || !in->asp || !in->resolution || !in->soil || !in->au))
         return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL per-cell input array");
-    if (nc > 0 && nd > 0 && (!in->sw_in || !in->tc || !in->pn || !in->year || !in->doy || !in->month))
-        return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL forcing/time array");
+    if (nd > 0 && (!in->year || !in->doy || !in->month)) return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL time array (year/doy/month)");
+    if (nc > 0 && nd > 0 && (!in->sw_in || !in->tc || !in->pn)) return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL forcing array");
     for (int64_t d = 0; d < nd; ++d)
         if (in->month[d] < 1 || in->month[d] > 12 || in->doy[d] < 1 || in->doy[d] > 366)
             return fail(ctx, SPLASH_ERR_BAD_ARG, "month/doy out of range at day %lld", (long long)d);
@@ -2459,6 +2698,9 @@ int splash_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts
         job.n_out = n_out;
         job.istride = istride;
         job.ostride = ostride;
+        job.apitch = apitch;
+        job.xpitch = xpitch;
+        job.spitch = spitch;
         job.in_dev = (in->mem_kind == SPLASH_MEM_DEVICE);
         job.out_dev = (out->mem_kind == SPLASH_MEM_DEVICE);
         job.monthly = opts.monthly_out != 0;
@@ -2522,3 +2764,292 @@ int splash_point_run(splash_ctx* ctx, int64_t n_days, const int32_t* year, const
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Block scheduler (splash_cluster_*): the reference's sendCall / recvOneData loop over its workers
+// (R/splash.grid.R:312-314, 359-400).  Lanes are single-GPU contexts with a worker thread each; blocks
+// wait in one FIFO and go to whichever lane is free next, as the reference's blocks go to whichever
+// worker has returned.  Cells are independent: lanes share nothing but the caller's (disjoint) arrays.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct ClusterJob {
+    int64_t ticket = 0;
+    splash_grid_in in{};
+    splash_opts opts{};
+    splash_grid_out out{};
+    int rc = SPLASH_OK;
+    splash_stats stats{};
+    std::string err;
+    bool done = false;
+};
+
+}  // namespace
+
+struct splash_cluster {
+    std::vector<splash_ctx*> lanes;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<ClusterJob*> fifo;
+    std::map<int64_t, ClusterJob*> jobs;  // submitted and not yet waited for
+    int64_t next_ticket = 1;
+    bool stop = false;
+    std::string err;
+    int n_devices = 0;
+};
+
+namespace {
+
+void cluster_worker(splash_cluster* cl, int lane) {
+    splash_ctx* ctx = cl->lanes[(size_t)lane];
+    for (;;) {
+        ClusterJob* job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(cl->mu);
+            cl->cv_work.wait(lk, [&] { return cl->stop || !cl->fifo.empty(); });
+            if (cl->fifo.empty()) return;  // stop requested and nothing left to run
+            job = cl->fifo.front();
+            cl->fifo.pop_front();
+        }
+        const int rc = splash_grid_run(ctx, &job->in, &job->opts, &job->out);
+        {
+            std::lock_guard<std::mutex> lk(cl->mu);
+            job->rc = rc;
+            job->stats = ctx->stats;
+            if (rc != SPLASH_OK) job->err = ctx->err;
+            job->done = true;
+        }
+        cl->cv_done.notify_all();
+    }
+}
+
+void add_stats(splash_stats& a, const splash_stats& b) {
+    a.h2d_ms = std::max(a.h2d_ms, b.h2d_ms);
+    a.setup_ms = std::max(a.setup_ms, b.setup_ms);
+    a.first_ms = std::max(a.first_ms, b.first_ms);
+    a.rounds_ms = std::max(a.rounds_ms, b.rounds_ms);
+    a.bulk_ms = std::max(a.bulk_ms, b.bulk_ms);
+    a.bulk_span_ms = std::max(a.bulk_span_ms, b.bulk_span_ms);
+    a.d2h_ms = std::max(a.d2h_ms, b.d2h_ms);
+    a.pool_wait_ms = std::max(a.pool_wait_ms, b.pool_wait_ms);
+    a.scatter_ms = std::max(a.scatter_ms, b.scatter_ms);
+    a.gpu_ms = std::max(a.gpu_ms, b.gpu_ms);
+    a.h2d_bytes += b.h2d_bytes;
+    a.d2h_bytes += b.d2h_bytes;
+    a.spin_cell_days += b.spin_cell_days;
+    a.main_cell_days += b.main_cell_days;
+    a.kernel_launches += b.kernel_launches;
+    a.unconverged_cells += b.unconverged_cells;
+    a.cycle_cells += b.cycle_cells;
+    a.n_tiles += b.n_tiles;
+    a.tile_cells = std::max(a.tile_cells, b.tile_cells);
+    a.pool_cells += b.pool_cells;
+    a.pool_overflow_cells += b.pool_overflow_cells;
+    a.pool_max_passes = std::max(a.pool_max_passes, b.pool_max_passes);
+}
+
+}  // namespace
+
+extern "C" {
+
+int splash_cluster_create(const int* devices, int n_devices, int lanes_per_device, splash_cluster** out) {
+    if (!out) return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_cluster_create: out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices <= 0 || n_devices > 64 || lanes_per_device <= 0 || lanes_per_device > 4)
+        return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_cluster_create: need 1..64 devices and 1..4 lanes per device");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_cluster_create: device %d listed twice", devices[i]);
+    splash_cluster* cl = new splash_cluster();
+    cl->n_devices = n_devices;
+    // lanes of one device are interleaved with the other devices' (lane l -> device l % n): the first blocks of a
+    // call spread over all GPUs
+    for (int l = 0; l < n_devices * lanes_per_device; ++l) {
+        splash_ctx* ctx = nullptr;
+        const int rc = splash_ctx_create(devices[l % n_devices], &ctx);
+        if (rc != SPLASH_OK) {
+            for (auto* c : cl->lanes) splash_ctx_destroy(c);
+            delete cl;
+            return rc;  // (the message is splash_last_error(NULL))
+        }
+        ctx->mem_share = 1.0 / lanes_per_device;
+        cl->lanes.push_back(ctx);
+    }
+    for (int l = 0; l < (int)cl->lanes.size(); ++l) cl->workers.emplace_back(cluster_worker, cl, l);
+    *out = cl;
+    return SPLASH_OK;
+}
+
+void splash_cluster_destroy(splash_cluster* cl) {
+    if (!cl) return;
+    {
+        std::lock_guard<std::mutex> lk(cl->mu);
+        cl->stop = true;
+    }
+    cl->cv_work.notify_all();
+    for (auto& t : cl->workers) t.join();  // outstanding blocks are run to completion first
+    for (auto& kv : cl->jobs) delete kv.second;
+    for (auto* c : cl->lanes) splash_ctx_destroy(c);
+    delete cl;
+}
+
+int splash_cluster_lanes(const splash_cluster* cl) { return cl ? (int)cl->lanes.size() : 0; }
+
+const char* splash_cluster_last_error(const splash_cluster* cl) { return cl ? cl->err.c_str() : g_create_err.c_str(); }
+
+int splash_cluster_submit(splash_cluster* cl, const splash_grid_in* in, const splash_opts* opts, const splash_grid_out* out,
+                          int64_t* ticket) {
+    if (!cl) return SPLASH_ERR_BAD_ARG;
+    if (!in || !out || !ticket) {
+        cl->err = "splash_cluster_submit: NULL in/out/ticket";
+        return SPLASH_ERR_BAD_ARG;
+    }
+    if (in->mem_kind != SPLASH_MEM_HOST || out->mem_kind != SPLASH_MEM_HOST) {
+        cl->err = "splash_cluster_submit: blocks of a cluster take HOST arrays (device arrays belong to one GPU: use splash_grid_run on that GPU's context)";
+        return SPLASH_ERR_BAD_ARG;
+    }
+    ClusterJob* job = new ClusterJob();
+    job->in = *in;
+    if (opts) job->opts = *opts;
+    job->out = *out;
+    {
+        std::lock_guard<std::mutex> lk(cl->mu);
+        job->ticket = cl->next_ticket++;
+        cl->jobs[job->ticket] = job;
+        cl->fifo.push_back(job);
+        *ticket = job->ticket;
+    }
+    cl->cv_work.notify_one();
+    return SPLASH_OK;
+}
+
+int splash_cluster_wait(splash_cluster* cl, int64_t ticket, int64_t* done_ticket, splash_stats* stats) {
+    if (!cl) return SPLASH_ERR_BAD_ARG;
+    std::unique_lock<std::mutex> lk(cl->mu);
+    ClusterJob* job = nullptr;
+    if (ticket >= 0) {
+        auto it = cl->jobs.find(ticket);
+        if (it == cl->jobs.end()) {
+            cl->err = "splash_cluster_wait: unknown ticket";
+            return SPLASH_ERR_BAD_ARG;
+        }
+        job = it->second;
+        cl->cv_done.wait(lk, [&] { return job->done; });
+    } else {
+        if (cl->jobs.empty()) {
+            cl->err = "splash_cluster_wait: nothing outstanding";
+            return SPLASH_ERR_BAD_ARG;
+        }
+        cl->cv_done.wait(lk, [&] {
+            for (auto& kv : cl->jobs)
+                if (kv.second->done) {
+                    job = kv.second;
+                    return true;
+                }
+            return false;
+        });
+    }
+    cl->jobs.erase(job->ticket);
+    if (done_ticket) *done_ticket = job->ticket;
+    if (stats) *stats = job->stats;
+    const int rc = job->rc;
+    if (rc != SPLASH_OK) cl->err = job->err;
+    delete job;
+    return rc;
+}
+
+int splash_ctx_create_multi(const int* devices, int n_devices, splash_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, SPLASH_ERR_BAD_ARG, "splash_ctx_create_multi: out_ctx is NULL");
+    *out_ctx = nullptr;
+    splash_cluster* cl = nullptr;
+    // two lanes per GPU: the upload of a block overlaps the tail (straggler chain) of the previous one
+    const int rc = splash_cluster_create(devices, n_devices, 2, &cl);
+    if (rc != SPLASH_OK) return rc;
+    splash_ctx* ctx = new splash_ctx();
+    ctx->device = devices[0];
+    ctx->multi = cl;
+    *out_ctx = ctx;
+    return SPLASH_OK;
+}
+
+int splash_ctx_device_count(const splash_ctx* ctx) { return !ctx ? 0 : (ctx->multi ? ctx->multi->n_devices : 1); }
+
+// splash_grid_run on a multi-GPU context: the block is cut into row blocks (two per lane, like
+// blockSize(minblocks = nodes * 2), R/splash.grid.R:264-268), which are scheduled over the lanes; every block
+// reads and writes its own cell range of the caller's arrays through the strides of the structs.
+static int multi_grid_run(splash_ctx* ctx, const splash_grid_in* in, const splash_opts* opts_in, splash_grid_out* out) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    ctx->err.clear();
+    ctx->stats = splash_stats{};
+    if (!in || !out) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_grid_run: NULL in/out");
+    if (in->mem_kind != SPLASH_MEM_HOST || out->mem_kind != SPLASH_MEM_HOST)
+        return fail(ctx, SPLASH_ERR_BAD_ARG, "a multi-GPU context takes HOST arrays (device arrays belong to one GPU)");
+    splash_opts opts{};
+    if (opts_in) opts = *opts_in;
+    const int64_t nc = in->n_cells;
+    if (nc < 0 || in->n_days < 0) return fail(ctx, SPLASH_ERR_BAD_ARG, "negative n_cells/n_days");
+    if (in->forcing_dtype != SPLASH_F64 && in->forcing_dtype != SPLASH_F32)
+        return fail(ctx, SPLASH_ERR_BAD_ARG, "forcing_dtype must be SPLASH_F64 or SPLASH_F32");
+    splash_cluster* cl = ctx->multi;
+    const int64_t fsz = in->forcing_dtype == SPLASH_F32 ? 4 : 8;
+    const int64_t istride = in->cell_stride ? in->cell_stride : nc, ostride = out->cell_stride ? out->cell_stride : nc;
+    const int64_t apitch = in->attr_stride ? in->attr_stride : nc, xpitch = out->aux_stride ? out->aux_stride : nc;
+    const int64_t spitch = opts.state_stride ? opts.state_stride : nc;
+    const int64_t lanes = (int64_t)cl->lanes.size();
+    int64_t n_blocks = std::max<int64_t>(1, std::min<int64_t>(2 * lanes, (nc + 4095) / 4096));
+    const int64_t bsz = std::max<int64_t>(1, round_up((nc + n_blocks - 1) / n_blocks, 1024));
+    n_blocks = nc > 0 ? (nc + bsz - 1) / bsz : 1;
+    int first_rc = SPLASH_OK;
+    std::vector<int64_t> tickets;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const int64_t b0 = b * bsz, n = std::max<int64_t>(0, std::min<int64_t>(bsz, nc - b0));
+        splash_grid_in bi = *in;
+        bi.n_cells = n;
+        bi.cell_stride = istride;
+        bi.attr_stride = apitch;
+        auto adv = [&](const void* p, int64_t bytes) { return p ? (const void*)((const char*)p + bytes) : nullptr; };
+        bi.sw_in = adv(in->sw_in, b0 * fsz);
+        bi.tc = adv(in->tc, b0 * fsz);
+        bi.pn = adv(in->pn, b0 * fsz);
+        bi.lat = (const double*)adv(in->lat, b0 * 8);
+        bi.elev = (const double*)adv(in->elev, b0 * 8);
+        bi.slop = (const double*)adv(in->slop, b0 * 8);
+        bi.asp = (const double*)adv(in->asp, b0 * 8);
+        bi.resolution = (const double*)adv(in->resolution, b0 * 8);
+        bi.soil = (const double*)adv(in->soil, b0 * 8);
+        bi.au = (const double*)adv(in->au, b0 * 8);
+        splash_grid_out bo = *out;
+        bo.cell_stride = ostride;
+        bo.aux_stride = xpitch;
+        double** layers[11] = {&bo.wn, &bo.ro, &bo.pet, &bo.aet, &bo.snow, &bo.cond, &bo.bflow, &bo.netr, &bo.sm_lim, &bo.state_final, &bo.cell_diag};
+        for (auto** q : layers)
+            if (*q) *q += b0;
+        splash_opts bopt = opts;
+        bopt.state_stride = spitch;
+        if (bopt.state_init) bopt.state_init += b0;
+        int64_t tk = 0;
+        const int rc = splash_cluster_submit(cl, &bi, &bopt, &bo, &tk);
+        if (rc != SPLASH_OK) {
+            first_rc = rc;
+            ctx->err = cl->err;
+            break;
+        }
+        tickets.push_back(tk);
+    }
+    for (int64_t tk : tickets) {
+        splash_stats st{};
+        const int rc = splash_cluster_wait(cl, tk, nullptr, &st);
+        if (rc != SPLASH_OK && first_rc == SPLASH_OK) {
+            first_rc = rc;
+            ctx->err = cl->err;
+        }
+        if (rc == SPLASH_OK) add_stats(ctx->stats, st);
+    }
+    ctx->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return first_rc;
+}
+
+}  // extern "C"
+
+static splash_ctx* first_lane(splash_ctx* ctx) { return ctx->multi->lanes[0]; }

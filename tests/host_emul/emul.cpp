@@ -93,6 +93,8 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
             else if (snowy) { ++n_snow; if (t > Tt) Tt = t; }
         }
         if (any_na) Tt = nan("");
+        const bool resume = opts && opts->skip_spinup && opts->state_init;
+        if (resume) Tt = opts->state_init[6 * nc + c];  // k_init_resume: the threshold the whole series was partitioned with
         cc(C_TT) = Tt;
         auto spin_forcing = [&](int d, double& sw, double& tc, double& pn) {
             if (d < nd) { sw = forcing(in->sw_in, d, c); tc = forcing(in->tc, d, c); pn = forcing(in->pn, d, c); }
@@ -106,7 +108,6 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
         DayOut o;
         double rain, snowfall, f_sw, f_tc, f_pn;
         int passes = 1;
-        const bool resume = opts && opts->skip_spinup && opts->state_init;
         if (resume) {  // k_init_resume: the carried state and aridity index instead of the spin-up
             const double* s0 = opts->state_init + c;
             st = CellState{s0[0 * nc], s0[1 * nc], s0[2 * nc], s0[3 * nc], s0[4 * nc]};
@@ -191,7 +192,7 @@ extern "C" int splash_emul_grid_run(const splash_grid_in* in, const splash_opts*
         }
         if (out->state_final) {
             double* s = out->state_final + c;
-            s[0 * nc] = st.wn; s[1 * nc] = st.snow; s[2 * nc] = st.qin; s[3 * nc] = st.td; s[4 * nc] = st.nd; s[5 * nc] = AI;
+            s[0 * nc] = st.wn; s[1 * nc] = st.snow; s[2 * nc] = st.qin; s[3 * nc] = st.td; s[4 * nc] = st.nd; s[5 * nc] = AI; s[6 * nc] = Tt;
         }
         if (diag) {
             diag[SPLASH_DIAG_TT * nc] = Tt; diag[SPLASH_DIAG_SNOW_DAYS * nc] = (double)n_snow; diag[SPLASH_DIAG_AI * nc] = AI;

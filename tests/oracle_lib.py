@@ -176,6 +176,21 @@ def run_cpu(problem: GridProblem, monthly=False, core="oracle", n_threads=0, sta
     return arrays
 
 
+def run_checked(problem: GridProblem, monthly=False, n_threads=0, state_init=None) -> dict:
+    """What the GPU results are compared with: the C restatement's result, asserted here to be bit-identical to the
+    compiled reference core (oracle/_ref: the unmodified SPLASH.cpp / EVAP.cpp / SOLAR.cpp) whenever that library
+    is present -- it travels to the GPU box -- so the comparison IS with the reference's own arithmetic.  (The
+    restatement also reports the spin-up pass counts, which the reference's spin_up does not return.)"""
+    a = run_cpu(problem, monthly=monthly, core="oracle", n_threads=n_threads, state_init=state_init)
+    a["checked_against_ref"] = False
+    if have_ref():
+        b = run_cpu(problem, monthly=monthly, core="ref", n_threads=n_threads, state_init=state_init)
+        for k in _abi.OUTPUT_NAMES + ("state_final",):
+            assert np.array_equal(a[k], b[k], equal_nan=True), f"C restatement differs from the compiled reference in {k}"
+        a["checked_against_ref"] = True
+    return a
+
+
 def unswc_cpu(soil, uns_depth, wn) -> dict:
     """unSWC.grid on the C restatement (R/unsSWC.grid.R): {theta_i, wtd, w_z, Se}, each [n_layers, n_cells]."""
     lib = oracle()

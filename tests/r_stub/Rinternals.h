@@ -23,6 +23,9 @@ double* REAL(SEXP x);
 int* INTEGER(SEXP x);
 int* LOGICAL(SEXP x);
 R_xlen_t XLENGTH(SEXP x);
+int TYPEOF(SEXP x);
+void R_PreserveObject(SEXP x);
+void R_ReleaseObject(SEXP x);
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v);

@@ -28,6 +28,11 @@ double* REAL(SEXP x) { need(x, REALSXP, "REAL()"); return (double*)x->data; }
 int* INTEGER(SEXP x) { if (!x || (x->type != INTSXP && x->type != LGLSXP)) Rf_error("stub: INTEGER() on a non-integer"); return (int*)x->data; }
 int* LOGICAL(SEXP x) { need(x, LGLSXP, "LOGICAL()"); return (int*)x->data; }
 R_xlen_t XLENGTH(SEXP x) { return x->len; }
+int TYPEOF(SEXP x) { return x ? x->type : NILSXP; }
+static int g_preserved = 0;
+void R_PreserveObject(SEXP) { ++g_preserved; }
+void R_ReleaseObject(SEXP) { --g_preserved; }
+int stub_preserved(void) { return g_preserved; }
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i) { need(x, VECSXP, "VECTOR_ELT()"); return ((SEXP*)x->data)[i]; }
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v) {
     need(x, VECSXP, "SET_VECTOR_ELT()");
@@ -141,7 +146,10 @@ SEXP stub_call(const char* name, int nargs, SEXP* a) {
             DL_FUNC f = g_call[i].fun;
             switch (nargs) {
                 case 0: return ((SEXP(*)(void))f)();
+                case 1: return ((SEXP(*)(SEXP))f)(a[0]);
                 case 4: return ((SEXP(*)(SEXP, SEXP, SEXP, SEXP))f)(a[0], a[1], a[2], a[3]);
+                case 16: return ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))f)(
+                    a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
                 case 15: return ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))f)(
                     a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14]);
                 default: g_err = "stub_call: unsupported arity"; return nullptr;

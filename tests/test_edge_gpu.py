@@ -22,10 +22,10 @@ def gpu(ctx, prob, dates, monthly=False, **kw):
 
 
 def check_vs_oracle(got, prob, ref=None):
-    ref = ref if ref is not None else ol.run_cpu(prob, monthly=False, core="oracle")
+    ref = ref if ref is not None else ol.run_checked(prob, monthly=False)  # == compiled reference core when oracle/_ref is there
     stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
     cells = np.flatnonzero(stable)
-    assert len(cells) >= 0.4 * prob.n_cells
+    assert len(cells) >= 0.5 * prob.n_cells
     sub = lambda r: {**{k: np.asarray(r[k])[:, cells] for k in _abi.OUTPUT_NAMES}, "cell_diag": np.asarray(r["cell_diag"])[:, cells]}
     parity.compare(sub(got), sub(ref))
     parity.compare_diag(sub(got)["cell_diag"], sub(ref)["cell_diag"])
@@ -51,7 +51,7 @@ def test_missing_values_propagate_per_layer(ctx):
     prob.sw_in[100:110, 24:32] = np.nan  # a gap in the radiation series
     prob.elev[32:40] = np.nan
     got = gpu(ctx, prob, dates)
-    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    ref = ol.run_checked(prob, monthly=False)
     for k in _abi.OUTPUT_NAMES:
         assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
     assert np.isnan(got["wn"][:, 0:24]).all() and np.isfinite(got["pet"][:, 16:24]).all()  # NA soil: radiation layers live
@@ -142,7 +142,7 @@ def test_tiny_lambda_on_dry_soil(ctx):
     n = prob.n_cells
     for row, (lo, hi) in enumerate([(5, 20), (38, 46), (1, 3), (20, 40), (1.45, 1.7)]):
         prob.soil[row] = rng.uniform(lo, hi, n).astype(np.float32)
-    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    ref = ol.run_checked(prob, monthly=False)
     lam = ref["cell_diag"][_abi.DIAG_NAMES.index("lambda")]
     assert (lam < 0.01).sum() >= 20
     check_vs_oracle(gpu(ctx, prob, dates), prob, ref)
@@ -153,6 +153,6 @@ def test_one_cell_and_one_day(ctx):
     one = ol.GridProblem(prob.year[:1], prob.doy[:1], prob.month[:1], prob.sw_in[:1], prob.tc[:1], prob.pn[:1], prob.lat, prob.elev,
                          prob.slop, prob.asp, prob.resolution, prob.soil, prob.au)
     got = gpu(ctx, one, dates[:1])
-    ref = ol.run_cpu(one, monthly=False, core="oracle")
+    ref = ol.run_checked(one, monthly=False)
     for k in _abi.OUTPUT_NAMES:
         assert got[k].shape == (1, 1) and np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k

@@ -1,4 +1,6 @@
-"""GPU parity: libsplash_cuda (through the C ABI) against the committed goldens and the live oracle."""
+"""GPU parity: libsplash_cuda (through the C ABI) against the committed goldens (outputs of the compiled reference)
+and against live runs of the checkers on this box: the C restatement, asserted bit-identical to the compiled
+reference core (oracle/_ref) in the same test."""
 import numpy as np
 import pytest
 
@@ -87,7 +89,8 @@ def _check_synthetic(ctx, n_cells, n_years, seed, max_unstable, **kw):
     from tests.synthetic import make_problem
 
     prob, dates = make_problem(n_cells=n_cells, n_years=n_years, seed=seed)
-    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    ref = ol.run_checked(prob, monthly=False)   # == the compiled reference core, asserted on this box (oracle/_ref travels)
+    assert ref["checked_against_ref"] or not ol.have_ref()
     sparse, knocked = conditioning.stable_cells(prob, ref, conditioning.SPARSE)
     dense, knocked_d = conditioning.stable_cells(prob, ref, conditioning.DENSE)
     dense &= sparse
@@ -101,7 +104,7 @@ def _check_synthetic(ctx, n_cells, n_years, seed, max_unstable, **kw):
           f"{int(dense.sum())} {knocked_d}; GPU outside the gates {int(gpu_off.sum())}, of which sparsely stable "
           f"{int((gpu_off & sparse).sum())}, densely stable {int((gpu_off & dense).sum())}")
     assert n_sparse_unstable <= max_unstable * n_cells, (n_sparse_unstable, knocked)
-    assert dense.sum() >= 0.3 * n_cells
+    assert dense.sum() >= 0.5 * n_cells
     cells = np.flatnonzero(dense)
     parity.compare(_subset(got, cells), _subset(ref, cells))
     parity.compare_diag(got["cell_diag"][:, cells], ref["cell_diag"][:, cells])

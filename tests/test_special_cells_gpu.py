@@ -39,6 +39,6 @@ def test_kernels_and_host_build_agree_on_the_special_cells(ctx):
     for k in ("wn", "snow", "ro", "bflow"):
         d = np.abs(got[k] - host[k])
         assert np.nanmax(d) <= 1e-9, (k, float(np.nanmax(d)))
-    ref = ol.run_cpu(prob, monthly=False, core="oracle")
+    ref = ol.run_checked(prob, monthly=False)
     assert np.array_equal(np.isnan(got["wn"]), np.isnan(ref["wn"]))
     assert (np.nanmax(np.abs(got["wn"] - ref["wn"]), axis=0) > 1e-6).sum() <= 2   # measured: 1 (ill-conditioned in the reference)

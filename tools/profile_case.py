@@ -20,9 +20,10 @@ prob, dates = make_problem(n_cells, n_years, seed=21)
 f32 = lambda a: a.astype(np.float32)  # the HBM layout of the benchmark (values are FP32-representable)
 kw = {}
 if mode == "bulk":
-    st = np.zeros((6, n_cells))
+    st = np.zeros((7, n_cells))
     st[0] = 0.5 * (prob.soil[5] * 300.0)  # a mid-range soil water content, mm
     st[5] = 1.5                           # aridity index carried in soil_info[12]
+    st[6] = 1.5                           # carried snowfall threshold temperature Tt
     kw = dict(state_init=st, tile_cells=n_cells)
 r = api.splash_grid(f32(prob.sw_in), f32(prob.tc), f32(prob.pn), prob.lat, prob.elev, prob.slop, prob.asp, prob.soil, prob.au,
                     prob.resolution, dates, monthly_out=True, **kw)
