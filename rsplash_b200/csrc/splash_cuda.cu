@@ -594,8 +594,21 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_run_bulk(RunParams p) {
         n_pn = ld_stream(pn_col);
     }
     for (int d = 0; d < p.n_days; ++d) {
+#ifdef SPLASH_NO_PREFETCH
+        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
+        if (live) {
+            f_sw = ld_stream(sw_col + (int64_t)d * p.fpitch);
+            f_tc = ld_stream(tc_col + (int64_t)d * p.tpitch);
+            f_pn = ld_stream(pn_col + (int64_t)d * p.fpitch);
+        }
+#else
         const double f_sw = n_sw, f_tc = n_tc, f_pn = n_pn;
+#endif
+#ifdef SPLASH_NO_PREFETCH
+        if (false) {
+#else
         if (live && d + 1 < p.n_days) {
+#endif
             const int64_t off = (int64_t)(d + 1) * p.fpitch;
             n_sw = ld_stream(sw_col + off);
             n_tc = ld_stream(tc_col + (int64_t)(d + 1) * p.tpitch);
@@ -1415,7 +1428,8 @@ struct splash_ctx {
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
     int64_t pool_cap = 0;                 // SPLASH_POOL_CAP: force the pool capacity (tests of the overflow path)
     int spin_ahead = 1;                   // SPLASH_SPIN_AHEAD=0: host-fed calls upload tile by tile (no spin-up data first)
-    int regime_sort = 1;                  // SPLASH_REGIME_SORT=0: the bulk launch takes the cells in grid order
+    int regime_sort = 0;                  // SPLASH_REGIME_SORT=1: the bulk launch takes the cells in regime-sorted order (measured
+                                          // slower on the synthetic grid, whose divergence is day-to-day weather: profiles/README.md)
     double mem_share = 1.0;               // share of the device's memory this context may plan with (lanes of a cluster)
     // a context over several GPUs (splash_ctx_create_multi): the work goes to the cluster's lanes
     splash_cluster* multi = nullptr;

@@ -49,6 +49,7 @@
 #include <type_traits>
 
 #include "splash_math.cuh"
+#include "splash_consts.cuh"
 
 namespace splash {
 
@@ -128,15 +129,19 @@ struct DayOut {
 
 #if SPLASH_L1_RECIP
 #define SPLASH_FDIV(a, b) fm::fdiv((a), (b))       // a/b to ~1.5 ulp, IEEE behaviour for 0/inf/NaN denominators
-#define SPLASH_DIVC(a, c) ((a) * (1.0 / (c)))      // division by a compile-time constant
-#define SPLASH_TO_DEG(x) ((x) * (180.0 / kPI))
+#define SPLASH_DIVC_1000(a) ((a) * kD.k_1em3)     // divisions by compile-time constants: a * (1.0 / c), the reciprocal
+#define SPLASH_DIVC_6(a) ((a) * kD.k_sixth)        // folded at compile time (and kept in constant memory)
+#define SPLASH_DIVC_1E6(a) ((a) * kD.k_1em6)
+#define SPLASH_TO_DEG(x) ((x) * kD.to_deg)
 #define SPLASH_DIV_D1000(x) ((x) * cc(C_INV_D1000))
 #define SPLASH_DIV_DTH(x) ((x) * cc(C_INV_DTH))
 #define SPLASH_DIV_TAU_B(x) ((x) * cc(C_INV_TAU_B))
-#define SPLASH_DIV_1000(x) ((x) * 1e-3)
+#define SPLASH_DIV_1000(x) ((x) * kD.k_1em3)
 #else
 #define SPLASH_FDIV(a, b) ((a) / (b))
-#define SPLASH_DIVC(a, c) ((a) / (c))
+#define SPLASH_DIVC_1000(a) ((a) / (1000.0))
+#define SPLASH_DIVC_6(a) ((a) / (6.0))
+#define SPLASH_DIVC_1E6(a) ((a) / (1e6))
 #define SPLASH_TO_DEG(x) ((x) / kpir)
 #define SPLASH_DIV_D1000(x) ((x) / cc(C_D1000))
 #define SPLASH_DIV_DTH(x) ((x) / cc(C_DTH))
@@ -181,7 +186,7 @@ __device__ __forceinline__ double snow_age_factor(double nd) {
 // h = acos(x) / pir; level 1 takes sin(acos(x)) = sqrt((1 - x)(1 + x)) instead (accurate to ~1.5 ulp for
 // every |x| < 1, no cancellation), and the reference's own values at the clamps: sin(0) = 0 and
 // sin(180 * pir) = sin(fl(pi)) = 1.2246467991473532e-16.
-#define SPLASH_SIN_180 1.2246467991473532e-16
+#define SPLASH_SIN_180 kD.sin_180
 
 // How the state half of the day step reaches its transcendentals.  MathShared: calls of the shared
 // out-of-line copies (the throughput kernels, where 16 warps per SM share the instruction cache).
@@ -230,8 +235,8 @@ __device__ __constant__ double kExp2Tab[32] = {
 __device__ __forceinline__ float glibc_expf(float x) {
     const double xd = (double)x;
     if (!(fabsf(x) < 88.0f)) return (float)f_exp(xd);  // overflow/underflow/NaN tails: not reached by viscosity
-    const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p+52;
-    const double C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13, C2 = 0x1.62e42ff0c52d6p-6;
+    const double InvLn2N = kD.ef_inv, Shift = 0x1.8p+52;
+    const double C0 = kD.ef_c0, C1 = kD.ef_c1, C2 = kD.ef_c2;
     double kd = fma(InvLn2N, xd, Shift);
     const uint64_t ki = (uint64_t)__double_as_longlong(kd);
     kd = kd - Shift;
@@ -256,31 +261,32 @@ struct DensityPoly {
 // temperature polynomials of EVAP::density_h2o, src/EVAP.cpp:349-378 (power sums as written)
 __device__ __forceinline__ DensityPoly density_poly(double tc) {
     DensityPoly q;
-    double po = 0.99983952;
-    po += (6.788260e-5) * tc;
-    po += -(9.08659e-6) * tc * tc;
-    po += (1.022130e-7) * tc * tc * tc;
-    po += -(1.35439e-9) * tc * tc * tc * tc;
-    po += (1.471150e-11) * tc * tc * tc * tc * tc;
-    po += -(1.11663e-13) * tc * tc * tc * tc * tc * tc;
-    po += (5.044070e-16) * tc * tc * tc * tc * tc * tc * tc;
-    po += -(1.00659e-18) * tc * tc * tc * tc * tc * tc * tc * tc;
-    double ko = 19652.17;
-    ko += 148.1830 * tc;
-    ko += -2.29995 * tc * tc;
-    ko += 0.01281 * tc * tc * tc;
-    ko += -(4.91564e-5) * tc * tc * tc * tc;
-    ko += (1.035530e-7) * tc * tc * tc * tc * tc;
-    double ca = 3.26138;
-    ca += (5.223e-4) * tc;
-    ca += (1.324e-4) * tc * tc;
-    ca += -(7.655e-7) * tc * tc * tc;
-    ca += (8.584e-10) * tc * tc * tc * tc;
-    double cb = (7.2061e-5);
-    cb += -(5.8948e-6) * tc;
-    cb += (8.69900e-8) * tc * tc;
-    cb += -(1.0100e-9) * tc * tc * tc;
-    cb += (4.3220e-12) * tc * tc * tc * tc;
+    // (the literals live in constant memory, splash_consts.cuh: same values, same operations)
+    double po = kD.po0;
+    po += kD.po1 * tc;
+    po += kD.po2 * tc * tc;
+    po += kD.po3 * tc * tc * tc;
+    po += kD.po4 * tc * tc * tc * tc;
+    po += kD.po5 * tc * tc * tc * tc * tc;
+    po += kD.po6 * tc * tc * tc * tc * tc * tc;
+    po += kD.po7 * tc * tc * tc * tc * tc * tc * tc;
+    po += kD.po8 * tc * tc * tc * tc * tc * tc * tc * tc;
+    double ko = kD.ko0;
+    ko += kD.ko1 * tc;
+    ko += kD.ko2 * tc * tc;
+    ko += kD.ko3 * tc * tc * tc;
+    ko += kD.ko4 * tc * tc * tc * tc;
+    ko += kD.ko5 * tc * tc * tc * tc * tc;
+    double ca = kD.ca0;
+    ca += kD.ca1 * tc;
+    ca += kD.ca2 * tc * tc;
+    ca += kD.ca3 * tc * tc * tc;
+    ca += kD.ca4 * tc * tc * tc * tc;
+    double cb = kD.cb0;
+    cb += kD.cb1 * tc;
+    cb += kD.cb2 * tc * tc;
+    cb += kD.cb3 * tc * tc * tc;
+    cb += kD.cb4 * tc * tc * tc * tc;
     q.po = po;
     q.ko = ko;
     q.ca = ca;
@@ -302,14 +308,13 @@ __device__ __forceinline__ double density_at(const DensityPoly& q, double pbar) 
 // EVAP::calc_viscosity_h2o, src/EVAP.cpp:405-462, with its FP32 roundings.  `tcf` is the float
 // the reference narrows tw to, `rho_d` = density_h2o((double)tcf, (double)pf) in double.
 __device__ __forceinline__ double viscosity_h2o(float tcf, double rho_d) {
-    const float tk_ast = 647.096f;
     const float rho = (float)rho_d;
-    const float tbar = (float)(((double)tcf + 273.15) / (double)tk_ast);
+    const float tbar = (float)(((double)tcf + kD.lv_a) / kD.vs_tk);
     const float tbarx = (float)sqrt((double)tbar);  // pow(tbar, 0.5) in double, narrowed
     const float tbar2 = tbar * tbar;
     const float tbar3 = tbar * tbar * tbar;
     const float rbar = rho / 322.0f;
-    float mu0 = (float)(1.67752 + 2.20462 / (double)tbar + 0.6366564 / (double)tbar2 - 0.241605 / (double)tbar3);
+    float mu0 = (float)(kD.vs_m0 + kD.vs_m1 / (double)tbar + kD.vs_m2 / (double)tbar2 - kD.vs_m3 / (double)tbar3);
     mu0 = (float)(1e2 * (double)tbarx / (double)mu0);
     const float ctbar = (float)((1.0 / (double)tbar) - 1.0);
     // integer powers of (rbar - 1.0) in double, j = 0..6
@@ -320,17 +325,18 @@ __device__ __forceinline__ double viscosity_h2o(float tcf, double rho_d) {
     const double ct2 = ct * ct, ct3 = ct2 * ct, ct4 = ct3 * ct, ct5 = ct4 * ct;
     // coef2_i = sum_j h[j][i] * (rbar-1)^j, accumulated in the reference's order with a float
     // round after every add; the table's zero entries add an exact 0 and are skipped.
-#define SPLASH_H(acc, h, p) acc = (float)((double)(acc) + (double)(h) * (p))
+    // (h: the float table entry widened to double, (double)0.520094f etc.; constant memory holds those doubles)
+#define SPLASH_H(acc, h, p) acc = (float)((double)(acc) + (h) * (p))
     float c2_0 = 0.0f, c2_1 = 0.0f, c2_2 = 0.0f, c2_3 = 0.0f, c2_4 = 0.0f, c2_5 = 0.0f;
-    SPLASH_H(c2_0, 0.520094f, 1.0); SPLASH_H(c2_0, 0.222531f, rb); SPLASH_H(c2_0, -0.281378f, rb2);
-    SPLASH_H(c2_0, 0.161913f, rb3); SPLASH_H(c2_0, -0.0325372f, rb4);
-    SPLASH_H(c2_1, 0.0850895f, 1.0); SPLASH_H(c2_1, 0.999115f, rb); SPLASH_H(c2_1, -0.906851f, rb2);
-    SPLASH_H(c2_1, 0.257399f, rb3);
-    SPLASH_H(c2_2, -1.08374f, 1.0); SPLASH_H(c2_2, 1.88797f, rb); SPLASH_H(c2_2, -0.772479f, rb2);
-    SPLASH_H(c2_3, -0.289555f, 1.0); SPLASH_H(c2_3, 1.26613f, rb); SPLASH_H(c2_3, -0.489837f, rb2);
-    SPLASH_H(c2_3, 0.0698452f, rb4); SPLASH_H(c2_3, -0.00435673f, rb6);
-    SPLASH_H(c2_4, -0.257040f, rb2); SPLASH_H(c2_4, 0.00872102f, rb5);
-    SPLASH_H(c2_5, 0.120573f, rb); SPLASH_H(c2_5, -0.000593264f, rb6);
+    SPLASH_H(c2_0, kD.h00, 1.0); SPLASH_H(c2_0, kD.h10, rb); SPLASH_H(c2_0, kD.h20, rb2);
+    SPLASH_H(c2_0, kD.h30, rb3); SPLASH_H(c2_0, kD.h40, rb4);
+    SPLASH_H(c2_1, kD.h01, 1.0); SPLASH_H(c2_1, (double)0.999115f, rb); SPLASH_H(c2_1, kD.h21, rb2);
+    SPLASH_H(c2_1, kD.h31, rb3);
+    SPLASH_H(c2_2, kD.h02, 1.0); SPLASH_H(c2_2, (double)1.88797f, rb); SPLASH_H(c2_2, kD.h22, rb2);
+    SPLASH_H(c2_3, kD.h03, 1.0); SPLASH_H(c2_3, kD.h13, rb); SPLASH_H(c2_3, kD.h23, rb2);
+    SPLASH_H(c2_3, (double)0.0698452f, rb4); SPLASH_H(c2_3, kD.h63, rb6);
+    SPLASH_H(c2_4, kD.h24, rb2); SPLASH_H(c2_4, kD.h54, rb5);
+    SPLASH_H(c2_5, kD.h15, rb); SPLASH_H(c2_5, kD.h65, rb6);
 #undef SPLASH_H
     float mu1 = 0.0f;
     mu1 = __fadd_rn(mu1, __fmul_rn(1.0f, c2_0));         // pow(ctbar, 0) == 1
@@ -349,16 +355,16 @@ __device__ __forceinline__ double viscosity_h2o(float tcf, double rho_d) {
 __device__ __forceinline__ double specific_heat(double tc) {
     double cp;
     if (tc < 0) {
-        cp = 1004.5714270;
+        cp = kD.cp_lo;
     } else if (tc > 100) {
-        cp = 2031.2260590;
+        cp = kD.cp_hi;
     } else {
-        cp = 1.0045714270;
-        cp += (2.050632750e-3) * tc;
-        cp += -(1.631537093e-4) * tc * tc;
-        cp += (6.212300300e-6) * tc * tc * tc;
-        cp += -(8.830478888e-8) * tc * tc * tc * tc;
-        cp += (5.071307038e-10) * tc * tc * tc * tc * tc;
+        cp = kD.cp0;
+        cp += kD.cp1 * tc;
+        cp += kD.cp2 * tc * tc;
+        cp += kD.cp3 * tc * tc * tc;
+        cp += kD.cp4 * tc * tc * tc * tc;
+        cp += kD.cp5 * tc * tc * tc * tc * tc;
         cp *= (1.0e3);
     }
     return cp;
@@ -386,7 +392,7 @@ __device__ __forceinline__ Transm column_transmittance_core(const CC& cc, double
     double wtd = SPLASH_DIV_1000(bub - psi_m);
     bool clamped = false;
     if (wtd < 0.0 || isnan(wtd)) {
-        wtd = 0.01;
+        wtd = kD.k_01b;
         clamped = true;
     } else if (wtd > depth) {
         wtd = depth;
@@ -400,7 +406,7 @@ __device__ __forceinline__ Transm column_transmittance_core(const CC& cc, double
         // the second base is 1 up to rounding noise (den == bub): first-order expansion
         const double q = SPLASH_FDIV(bub, den);
         const double qm1 = q - 1.0;
-        const double r2 = (fabs(qm1) < 1e-7) ? (1.0 + e3 * qm1) : M::exp(e3 * M::log(q));
+        const double r2 = (fabs(qm1) < kD.k_1em7) ? (1.0 + e3 * qm1) : M::exp(e3 * M::log(q));
         dr = r1 - r2;
     } else {
         // wtd was clamped: on dry soil both bases are x^(1/lambda)-small and differ by depth/psi_m ~ 1e-15 relative.
@@ -408,7 +414,7 @@ __device__ __forceinline__ Transm column_transmittance_core(const CC& cc, double
         // below is tiny or exactly 0 decides between a finite and an infinite t_drain (:1470).  The ratio form
         // r1 * ((den_ratio)^e3 - 1) keeps it, as the reference's two pow() of nearly equal bases do.
         const double t = e3 * M::log(SPLASH_FDIV(psi_m, den));
-        const double em1 = (fabs(t) < 1e-5) ? t * (1.0 + 0.5 * t) : M::exp(t) - 1.0;
+        const double em1 = (fabs(t) < kD.k_1em5) ? t * (1.0 + 0.5 * t) : M::exp(t) - 1.0;
         dr = -(r1 * em1);
     }
     double t_uns = (ksat_visc * bub / e3) * dr;
@@ -450,10 +456,10 @@ __device__ __forceinline__ Transm column_transmittance(const CC& cc, double sm, 
 // written.  Returns -1 (NA), 1 (snow-probable day) or 0.
 template <class CC>
 __device__ __forceinline__ int snow_class(const CC& cc, double tc) {
-    const double z = -0.4710405934 + 1.0473543991 * tc - cc(C_ELEV_K) - cc(C_LAT_K);
+    const double z = kD.snow_a + kD.snow_b * tc - cc(C_ELEV_K) - cc(C_LAT_K);
     if (isnan(z)) return -1;
-    if (z < -1e-9) return 1;
-    if (z > 1e-9) return 0;
+    if (z < kD.snow_lo) return 1;
+    if (z > kD.snow_hi) return 0;
     return (1 / (1 + exp(z)) >= 0.5) ? 1 : 0;
 }
 
@@ -492,7 +498,7 @@ struct DayPre {
 };
 constexpr int kDayPreDoubles = sizeof(DayPre) / sizeof(double);
 
-template <class CC>
+template <class M = MathShared, class CC>
 __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
                                             double pn, DayPre& q) {
     // ---- snow partition, R/splash.point.R:120-128 with frain_func :547-555 ------------------------
@@ -506,9 +512,9 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         const double x = SPLASH_FDIV(tc - Ttm, mt.trm14[dt.month]);
         double frain;
         if (tc <= Ttm) {
-            frain = 5 * (x * x * x) + 6.76 * (x * x) + 3.19 * x + 0.5;
+            frain = 5 * (x * x * x) + kD.fr_a * (x * x) + kD.fr_b * x + 0.5;
         } else {
-            frain = 5 * (x * x * x) - 6.76 * (x * x) + 3.19 * x + 0.5;
+            frain = 5 * (x * x * x) - kD.fr_a * (x * x) + kD.fr_b * x + 0.5;
         }
         if (frain < 0) frain = 0;
         if (frain > 1) frain = 1;
@@ -545,7 +551,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         sin_hs = 0.0;
     } else {
         const double x = -1.0 * ruv;
-        hs = SPLASH_TO_DEG(f_acos(x));
+        hs = SPLASH_TO_DEG(M::acos(x));
         sin_hs = sqrt((1.0 - x) * (1.0 + x));
     }
 #else
@@ -560,8 +566,8 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     }
     const double sin_hs = f_sin(hs * kpir);
 #endif
-    double ra_d = (86400.0 / kPI) * dt.dr * kGsc;
-    ra_d *= (ru * hs * kpir + rv * sin_hs);
+    double ra_d = kD.k_ra * dt.dr * kD.gsc;
+    ra_d *= (ru * hs * kD.pir + rv * sin_hs);
     const double tau_o = cc(C_TAU_O);
     const double r_in = 86400 * sw_in;
     double tau;
@@ -571,7 +577,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         tau = SPLASH_FDIV(r_in, ra_d);
     }
 #if SPLASH_L1_POW
-    double sf = f_exp((1 / 0.7410) * f_log(SPLASH_DIV_TAU_B(tau - cc(C_TAU_A))));
+    double sf = M::exp(kD.sf_exp * M::log(SPLASH_DIV_TAU_B(tau - cc(C_TAU_A))));
 #else
     double sf = pow(((tau - cc(C_TAU_A)) / cc(C_TAU_B)), (1 / 0.7410));
 #endif
@@ -580,7 +586,7 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     } else if (sf > 1.0) {
         sf = 1.0;
     }
-    q.rnl = (0.0883289 + (1.0 - kb) * sf) * (kA + 1.95974 * tc);
+    q.rnl = (kD.rnl_a + kD.rnl_b * sf) * (kD.rnl_A + kD.rnl_c * tc);
     q.ru = ru;
     q.rv = rv;
     q.ruv = ruv;
@@ -589,21 +595,21 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.tau = tau;
     q.dr = dt.dr;
     q.r_in = r_in;
-    q.rw_den = ((86400.0 / kPI) * (ru * kpir * hs + rv * sin_hs));
+    q.rw_den = (kD.k_ra * (ru * kD.pir * hs + rv * sin_hs));
     q.rw_dark = ((sw_in == 0.0) || (hs == 0.0)) ? 1.0 : 0.0;
 
     // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:100-145 --------------------------------------------
     const double patm = cc(C_PATM);
-    double s = f_exp(SPLASH_FDIV(tc * 17.269, tc + 237.3));  // sat_slope, :299-301
-    s = SPLASH_FDIV(s, (tc + 237.3) * (tc + 237.3));
-    s *= (17.269) * (237.3) * (610.78);
-    double lv = SPLASH_FDIV(tc + 273.15, tc + 273.15 - 33.91);  // enthalpy_vap, :313-315
+    double s = M::exp(SPLASH_FDIV(tc * kD.ss_a, tc + kD.ss_b));  // sat_slope, :299-301
+    s = SPLASH_FDIV(s, (tc + kD.ss_b) * (tc + kD.ss_b));
+    s *= kD.ss_k;
+    double lv = SPLASH_FDIV(tc + kD.lv_a, tc + kD.lv_a - kD.lv_b);  // enthalpy_vap, :313-315
     lv = lv * lv;
     lv *= 1.91846e6;
     const DensityPoly qd = density_poly(tc);
     const double pw = density_at(qd, cc(C_PBAR));
     const double cp = specific_heat(tc);
-    const double g = SPLASH_FDIV(kMa * cp * patm, kMv * lv);  // psychro, :486
+    const double g = SPLASH_FDIV(kD.ma * cp * patm, kD.mv * lv);  // psychro, :486
     const double econ = SPLASH_FDIV(s, lv * pw * (s + g));
     // viscosity at tw = max(tc, 0) narrowed to float, :100-105,120,413
     double visc;
@@ -623,9 +629,9 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.g = g;
     q.econ = econ;
     q.pw = pw;
-    q.eet_k = (1.0e3) * SPLASH_FDIV(s, lv * pw * (s + 0.24 * g));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
+    q.eet_k = (1.0e3) * SPLASH_FDIV(s, lv * pw * (s + kD.eet_c * g));  // EVAP.cpp:129-131: eet_d = eet_k * rn_d
     q.rx = (3.6e6) * econ;
-    q.ksat_visc = cc(C_INTPERM) * SPLASH_FDIV(pw * kG, visc) * 3.6;  // SPLASH.cpp:1260
+    q.ksat_visc = cc(C_INTPERM) * SPLASH_FDIV(pw * kD.grav, visc) * kD.k36;  // SPLASH.cpp:1260
 #if SPLASH_L1_RECIP
     q.inv_rw_den = SPLASH_FDIV(1.0, q.rw_den);
     q.inv_rx = SPLASH_FDIV(1.0, q.rx);
@@ -644,9 +650,9 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double theta_mean = SPLASH_DIV_D1000(wn);
     double theta_i = theta_mean;
     if (theta_i >= theta_s) {
-        theta_i = theta_s - 0.001;
+        theta_i = theta_s - kD.k_001;
     } else if (theta_i <= cc(C_THR)) {
-        theta_i = cc(C_THR) + 0.001;
+        theta_i = cc(C_THR) + kD.k_001;
     }
 #if SPLASH_L1_RECIP
     double sw = ((wn - cc(C_RES)) * cc(C_INV_WMR));
@@ -669,13 +675,13 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 
     // ---- SOLAR::calculate_daily_fluxes, SOLAR.cpp:208-255 ------------------------------------------
     const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
-    const double max_alb_snw = (1.0 - 0.443700) + (0.443700 * snow_age_factor(nd));
+    const double max_alb_snw = kD.alb_a + (kD.alb_b * snow_age_factor(nd));
     const double sfc = SPLASH_FDIV(snow, 140.0 + snow);
-    const double alb_v = kalb_sw - 0.17 * sw;
+    const double alb_v = kD.alb_sw - kD.alb_c * sw;
     const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
     double rw;
     if (q.rw_dark != 0.0) {
-        rw = (1.0 - alb) * q.tau * q.dr * kGsc;
+        rw = (1.0 - alb) * q.tau * q.dr * kD.gsc;
     } else {
 #if SPLASH_L1_RECIP
         rw = (1.0 - alb) * (q.r_in) * q.inv_rw_den;
@@ -713,16 +719,16 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     }
     const double sin_hn = M::sin(hn * kpir);
 #endif
-    double rn_d = kpir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
-    rn_d *= (86400.0 / kPI);
+    double rn_d = kD.pir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
+    rn_d *= kD.k_ra;
     double rnn_d = rw * rv * (sin_hs - sin_hn);
-    rnn_d += rw * ru * (hs - hn) * kpir;
-    rnn_d -= rnl * (kPI - hn * kpir);
-    rnn_d *= (86400.0 / kPI);
+    rnn_d += rw * ru * (hs - hn) * kD.pir;
+    rnn_d -= rnl * (kD.k_pi - hn * kD.pir);
+    rnn_d *= kD.k_ra;
 
     // ---- EVAP::calculate_daily_fluxes, EVAP.cpp:124-263 --------------------------------------------
     const double s = q.s, g = q.g, econ = q.econ, pw = q.pw, rx = q.rx;
-    const double cn = (1.0e3) * econ * fabs(rnn_d) * 0.1;
+    const double cn = (1.0e3) * econ * fabs(rnn_d) * kD.k_01;
     const double eet_d = q.eet_k * rn_d;
     const double pet_max = rx * ((rw * (ru + rv)) - rnl);
 #if SPLASH_L1_RECIP
@@ -775,18 +781,18 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     } else {
         snowmelt_tot = 0.0;
     }
-    double melt_enrg = SPLASH_DIVC(snowmelt_tot, 1000.0) * pw * kkfus;
+    double melt_enrg = SPLASH_DIVC_1000(snowmelt_tot) * pw * kkfus;
     const double AE = rn_d - melt_enrg;
     const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
 #if SPLASH_L1_RECIP
-    melt_enrg += SPLASH_DIVC(sublimation, 1000.0) * q.inv_econ;
+    melt_enrg += SPLASH_DIVC_1000(sublimation) * q.inv_econ;
 #else
-    melt_enrg += SPLASH_FDIV(SPLASH_DIVC(sublimation, 1000.0), econ);
+    melt_enrg += SPLASH_FDIV(SPLASH_DIVC_1000(sublimation), econ);
 #endif
-    double aet_d = swp * hi * kpir;
+    double aet_d = swp * hi * kD.pir;
     aet_d += rx * rw * rv * (sin_hn - sin_hi);
-    aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kpir;
-    aet_d *= (24.0 / kPI);
+    aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kD.pir;
+    aet_d *= kD.k_24pi;
 #if SPLASH_L1_RECIP
     // Days without melt and without an evaporation integral (polar night): sublimation = (AE*econ)*1000 is negative
     // (deposition) and aet becomes ((sublimation/1000)/econ * econ) * 1000 -- the same operations run backwards and
@@ -819,7 +825,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         double head = inv_u + cc(C_TEN_BP);
         // the reference forms bp/u first (:1945), which overflows to -inf once |bp|/u > DBL_MAX (dry soil with a
         // tiny lambda: u = x^(1/lambda) ~ 1e-306); head/bp is then +inf and theta_BC collapses onto theta_r
-        if (inv_u > fabs(cc(C_TEN_BP)) * 1.7976931348623157e307) head = INFINITY;
+        if (inv_u > fabs(cc(C_TEN_BP)) * kD.k_ovf) head = INFINITY;
         double hp = M::exp(cc(C_NLAM) * M::log(head));
         // an air-entry pressure of exactly 0 (pedotransfer result of some sandy, gravelly soils) makes the base -inf:
         // pow(-inf, y) is +0 for y < 0, +inf for y > 0 and 1 for y == 0 (C11 F.10.4.4), not NaN
@@ -843,7 +849,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     double infi;
     {
         const double P = inflow;
-        const double r = SPLASH_DIVC(P, 6.0);
+        const double r = SPLASH_DIVC_6(P);
         const double h_f = cc(C_HF);
         const double delta_theta = (theta_s - surf_moist);
         double I = 0.0;
@@ -855,7 +861,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
             } else {
                 double tp = SPLASH_FDIV(Ksat_visc * delta_theta * -1.0 * h_f, r * (r - Ksat_visc));
                 if (tp <= 0.0 || isnan(tp)) {
-                    tp = 0.01;
+                    tp = kD.k_01b;
                 }
                 const double tp_s = tp / cc(C_COS2_S);
                 I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * M::log(1 - SPLASH_FDIV(r * tp_s, h_f * delta_theta))));
@@ -891,7 +897,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     const double kbe3 = (Ksat_visc * cc(C_BUB) / cc(C_E3));
     const double T_q0 = kbe3 * cc(C_BRQ0);
     const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
-    const double Q_qs = SPLASH_DIVC(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS), 1000.0);
+    const double Q_qs = SPLASH_DIVC_1000(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS));
 #if SPLASH_L1_RECIP
     // 5.7 takes log(Kb) back (:1470): on gentle slopes the exponent is ~1e-8 and every bit of Kb counts.  There
     // 1 + z + z^2/2 rounds to the correctly rounded exp(z) (as glibc's exp does) with probability 1 - |z|.
@@ -903,7 +909,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     // ---- 5.2.2 drainage at Wmax, :1346-1360 --------------------------------------------------------
     const double To_uns = kbe3 * cc(C_BRW);
     const double Qo_uns = To_uns * cc(C_CW);
-    const double Qo_sat = SPLASH_DIVC(Ksat_visc * 24.0 * cc(C_ACSW), 1000.0);
+    const double Qo_sat = SPLASH_DIVC_1000(Ksat_visc * 24.0 * cc(C_ACSW));
     const double Qt = (Qo_sat + Qo_uns) * hyd_grad_out;
     // ---- 5.2.3 upslope input of the previous day, :1365-1372 ---------------------------------------
     double q_in_o = 0.0;
@@ -946,7 +952,7 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
         }
         T = (T_sat + T_uns) * hyd_grad_out;
     }
-    const double Q = SPLASH_DIVC(T * Ai, 1000.0);
+    const double Q = SPLASH_DIVC_1000(T * Ai);
     // ---- 5.7 same-day upslope input, :1465-1483 ----------------------------------------------------
     double t_drain = 0.0;
     double q_in_f = 0.0;
@@ -998,21 +1004,28 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
     o.aet = aet_d;
     o.cond = cn;
     o.bflow = T;
-    o.netr = SPLASH_DIVC(rn_d, 1e6);
+    o.netr = SPLASH_DIVC_1E6(rn_d);
 #undef SPLASH_DIV_AI
 }
 
 //   st     state in/out;  o  fluxes of the day;  rain_out / snowfall_out  the partitioned precipitation
 //   (for the aridity index and the occurrence flags)
+// SPLASH_UNIFORM_INLINE (experiment): the uniform kernels expand the transcendentals in place as the chain kernel does
+#ifdef SPLASH_UNIFORM_INLINE
+using DayMath = MathInline;
+#else
+using DayMath = MathShared;
+#endif
+
 template <class CC>
 __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const MonthTab& mt, double sw_in, double tc,
                                            double pn, CellState& st, DayOut& o, double& rain_out,
                                            double& snowfall_out) {
     DayPre q;
-    day_forcing(cc, dt, mt, sw_in, tc, pn, q);
+    day_forcing<DayMath>(cc, dt, mt, sw_in, tc, pn, q);
     rain_out = q.rain;
     snowfall_out = q.snowfall;
-    day_state(cc, q, st, o);
+    day_state<DayMath>(cc, q, st, o);
 }
 
 // ------------------------------------------------------------------------------------------------

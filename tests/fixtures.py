@@ -75,7 +75,7 @@ def f32_round(a):
 def load_problem(name: str) -> tuple[ol.GridProblem, np.ndarray]:
     """-> (GridProblem, dates[datetime64 D]) for 'bourne', 'atneu' or 'sacru'."""
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}_inputs.npz"))
-    if name == "sacru":
+    if name in ("sacru", "sacru_full"):  # sacru_full: every non-ocean cell of the 22 101-cell grid (6153)
         days = np.arange(np.datetime64("2014-01-01"), np.datetime64("2017-01-01"))
         mstart = np.arange(np.datetime64("2014-01"), np.datetime64("2017-01")).astype("datetime64[D]")
         di, mi = days.astype(np.int64), mstart.astype(np.int64)

@@ -16,7 +16,7 @@ _libs = {}
 def build(level: int = 1) -> str:
     out = os.path.join(ROOT, "tests", "_build", f"libsplash_emul_l{level}.so")
     deps = [os.path.join(SRC_DIR, f) for f in ("emul.cpp", "cuda_runtime.h")] + \
-           [os.path.join(CSRC, f) for f in ("splash_model.cuh", "splash_math.cuh", "splash_host_tables.h")] + \
+           [os.path.join(CSRC, f) for f in ("splash_model.cuh", "splash_math.cuh", "splash_consts.cuh", "splash_host_tables.h")] + \
            [os.path.join(ROOT, "include", "splash_cuda.h")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out

@@ -46,8 +46,20 @@ def test_host_build_reproduces_the_reference_goldens(name):
     parity.compare_diag(got["cell_diag"], gold["cell_diag"])
 
 
+def test_host_build_meets_the_gates_on_every_cell_of_the_full_sacru_grid():
+    """configs[2]: the package's CRU example, EVERY non-ocean cell of its 22 101-cell grid (6152; the other cells are
+    all-NA in and out), every day, no conditioning filter -- against the compiled reference core run here."""
+    prob, dates = load_problem("sacru_full")
+    assert prob.n_cells == 6152
+    ref = ol.run_checked(prob, monthly=False)
+    got = he.run(prob)
+    parity.compare(got, ref)
+    parity.compare_diag(got["cell_diag"], ref["cell_diag"])
+
+
 def test_host_build_reproduces_the_sacru_grid_golden():
-    """22 101 cells of the package's CRU example (tests/golden/sacru_*): daily layers of the probe cells, all diagnostics."""
+    """A 545-cell subset of the package's CRU example with committed outputs of the compiled reference
+    (tests/golden/sacru_*: every mismatched-NA cell, every 12th valid cell): daily layers of the probe cells, all diagnostics."""
     prob, dates = load_problem("sacru")
     gold = load_golden("sacru")
     probe = np.load(GOLDEN_DIR + "/sacru_probe.npz")["probe"]

@@ -40,6 +40,7 @@ def test_point_fixture_monthly_matches_reference_golden(ctx, name):
 
 
 def test_sacru_grid_matches_reference_golden(ctx):
+    """(a 545-cell subset with committed reference outputs; the whole grid is the next test)"""
     prob, dates = fx.load_problem("sacru")
     gold = fx.load_golden("sacru")
     probe = np.load(fx.GOLDEN_DIR + "/sacru_probe.npz")["probe"]
@@ -49,6 +50,21 @@ def test_sacru_grid_matches_reference_golden(ctx):
     sub = {k: got_d[k][:, probe] for k in _abi.OUTPUT_NAMES}
     parity.compare(sub, gold, prefix="daily_")
     parity.compare_diag(got_d["cell_diag"], gold["cell_diag"])
+
+
+def test_full_sacru_grid_matches_the_live_reference(ctx):
+    """BASELINE configs[2], whole grid: every non-ocean cell of data(SA_cru) (6152 of 22 101; the rest is all-NA), daily
+    and monthly, no conditioning filter, against the compiled reference core (oracle/_ref) run on this box."""
+    prob, dates = fx.load_problem("sacru_full")
+    assert prob.n_cells == 6152
+    ref = ol.run_checked(prob, monthly=False)
+    assert ref["checked_against_ref"] or not ol.have_ref()
+    got = run_gpu(ctx, prob, dates, monthly=False)
+    rep = parity.compare(got, ref)
+    parity.compare_diag(got["cell_diag"], ref["cell_diag"])
+    parity.compare(run_gpu(ctx, prob, dates, monthly=True), ol.run_cpu(prob, monthly=True, core="ref" if ol.have_ref() else "oracle"),
+                   monthly=True)
+    print("full SA_cru", rep)
 
 
 def test_sacru_f32_forcing_path_is_identical(ctx):

@@ -131,6 +131,13 @@ def sacru():
     np.savez_compressed(os.path.join(OUT, "sacru_inputs.npz"), cell_index=keep, tc_monthly=f4(tc_m[:, keep]),
                         pn_monthly=f4(pn_m[:, keep]), sw_monthly=f4(sw_m[:, keep]), lat=lat[keep], elev=elev[keep],
                         resolution=res, soil=soil[:, keep], n_all_valid=int(allv.sum()), n_partial=len(odd))
+    # the FULL grid's inputs: every cell with any valid layer (6153 of 22101; the rest is ocean: all-NA in, all-NA out).
+    # No stored outputs: tests run the compiled reference core live on these cells (oracle/_ref travels to the GPU box).
+    full = np.flatnonzero(anyv)
+    res_f = np.sqrt((111.32 * 0.5) * (111.32 * 0.5 * np.cos(np.deg2rad(lat[full])))) * 1000.0
+    np.savez_compressed(os.path.join(OUT, "sacru_full_inputs.npz"), cell_index=full, tc_monthly=f4(tc_m[:, full]),
+                        pn_monthly=f4(pn_m[:, full]), sw_monthly=f4(sw_m[:, full]), lat=lat[full], elev=f4(elev[full]),
+                        resolution=res_f, soil=f4(soil[:, full]), n_all_valid=int(allv.sum()), n_grid_cells=ncell)
     prob, days = fx.load_problem("sacru")  # the deterministic daily series both sides will see
     probe = np.concatenate([np.flatnonzero(np.isin(keep, odd)), np.arange(0, n, 41)])
     probe = np.unique(probe)
