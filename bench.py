@@ -16,9 +16,9 @@ A step is one whole-job pass of the hot path over the rank's shard:
     value  inputs resident in HBM (forcing stored as f32 -- lossless, the rasters are FLT4S -- all
            arithmetic f64), outputs written to HBM; timed around splash_grid_run(DEVICE pointers)
     e2e    the same job through the C ABI with HOST buffers (pinned, f64 like R's REAL()): the shard is fed
-           block of rows by block of rows through the block scheduler (splash_cluster_submit / _wait, the
-           reference's sendCall / recvOneData, R/splash.grid.R:312-314, 359-400), host->device and
-           device->host copies inside the timed region.  At most 3 timed passes (`e2e.steps`).
+           block of rows by block of rows as the reference's clFun scheduler does (R/splash.grid.R:264-268),
+           host->device and device->host copies inside the timed region.  At most 3 timed passes (`e2e.steps`);
+           each pinned block is staged once and run for all of them.
 The numerator is the job size as the reference defines it: n_cells * n_days plus the spin-up cell-days its
 algorithm requires (365 for the aridity pass + passes * 366 per cell); `config.executed_*` quote the
 cell-days the GPU actually simulated (exact cycle skipping removes work).
@@ -72,7 +72,6 @@ def parse_args(argv=None):
     ap.add_argument("--cells", type=int, default=synthetic.N_CELLS_5ARCMIN)
     ap.add_argument("--years", type=int, default=10)
     ap.add_argument("--e2e-blocks", type=int, default=0, help="row blocks per rank for the e2e leg (0 = auto)")
-    ap.add_argument("--e2e-lanes", type=int, default=4, help="calls in flight per GPU in the e2e leg")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="cells of the CPU baseline / parity sample")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -380,7 +379,7 @@ def main():
     import torch.distributed as dist
 
     from rsplash_b200 import build
-    from rsplash_b200._lib import Cluster, Context
+    from rsplash_b200._lib import Context
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libsplash_cuda has no CPU path (use --impl reference for the CPU arm)")
@@ -526,58 +525,54 @@ def main():
     e2e = None
     if not args.no_e2e:
         t0 = time.perf_counter()
-        ctx.close()  # the lanes of the cluster own the device from here on
         # pinned f64 forcing: at most ~45 % of what the host has free, shared by the ranks of the box
-        pin_budget = 110e9
+        pin_budget = 76e9
         try:
             avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
-            pin_budget = min(pin_budget, 0.45 * avail / world)
+            pin_budget = min(pin_budget, 0.40 * avail / world)
         except Exception:
             pass
-        lanes = max(1, args.e2e_lanes)
-        n_buf = lanes + 2                                   # pinned block buffers: the blocks in flight plus two being refilled
+        # One pinned block at a time, as large as the budget allows (fewer calls = fewer exposed straggler tails): the
+        # block is staged once, then run for the warm-up and every timed pass; a pass is the sum over the blocks.
         per_cell = nd * 3 * 8 + n_out * 9 * 8 + 14 * 8
-        bsz = int(min(nc, max(1024, (pin_budget / n_buf / per_cell) // 1024 * 1024)))
+        bsz = int(min(nc, max(1024, (pin_budget / per_cell) // 1024 * 1024)))
         if args.e2e_blocks:
             bsz = int(np.ceil(nc / args.e2e_blocks / 1024) * 1024)
         else:  # equal blocks
             bsz = int(np.ceil(nc / np.ceil(nc / bsz) / 1024) * 1024)
         n_blocks = int(np.ceil(nc / bsz))
-        n_buf = min(n_buf, n_blocks)
         pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
-        bufs = [{"f": [pin(nd, bsz) for _ in range(3)], "out": [pin(n_out, bsz) for _ in range(9)],
-                 "cells": {k: np.zeros((v.shape[0], bsz) if v.ndim == 2 else (bsz,)) for k, v in shard_cells_np.items()
-                           if k in ("lat", "elev", "slop", "asp", "resolution", "soil", "au")}} for _ in range(n_buf)]
-        chunk_days = max(1, int(1e9 // (bsz * 8 * 3)))
-        side = torch.cuda.Stream(device=device)             # staging never waits for the lanes' work (no device-wide sync)
-        with torch.cuda.stream(side):
-            d_chunk = [torch.empty((chunk_days, bsz), dtype=torch.float64, device=device) for _ in range(3)]
+        buf = {"f": [pin(nd, bsz) for _ in range(3)], "out": [pin(n_out, bsz) for _ in range(9)],
+               "cells": {k: np.zeros((v.shape[0], bsz) if v.ndim == 2 else (bsz,)) for k, v in shard_cells_np.items()
+                         if k in ("lat", "elev", "slop", "asp", "resolution", "soil", "au")}}
+        bufs = [buf]
+        chunk_days = max(1, int(2e9 // (bsz * 8 * 3)))
+        d_chunk = [torch.empty((chunk_days, bsz), dtype=torch.float64, device=device) for _ in range(3)]
         hopts = _abi.SplashOpts()
         hopts.monthly_out = 1
         phases["e2e_alloc_s"] = time.perf_counter() - t0
 
-        def stage(b, buf):
-            """block b's inputs into pinned host memory: the caller's data (generated on the device, copied out)"""
+        def stage(b):
+            """block b's inputs into pinned host memory (untimed: this is the caller's data): generated on the device, copied out"""
             b0, b1 = b * bsz, min(nc, (b + 1) * bsz)
             n = b1 - b0
             idx = shard_index[b0:b1]
             # contiguous runs of global cells inside the block (shard boundaries of the round-robin deal)
             cuts = np.flatnonzero(np.diff(idx) != 1) + 1
             runs = np.split(np.arange(n), cuts)
-            with torch.cuda.stream(side):
-                for d0 in range(0, nd, chunk_days):
-                    d1 = min(nd, d0 + chunk_days)
-                    for r in runs:
-                        sub = {k: (v[..., b0 + r[0]:b0 + r[-1] + 1] if isinstance(v, np.ndarray) else v) for k, v in shard_cells_np.items()}
-                        filler.fill(sub, d_chunk[0][:, r[0]:], d_chunk[1][:, r[0]:], d_chunk[2][:, r[0]:], day0=d0, n_days=d1 - d0)
-                    for h, dsrc in zip(buf["f"], d_chunk):
-                        h[d0:d1, :n].copy_(dsrc[:d1 - d0, :n], non_blocking=True)
-                    side.synchronize()
+            for d0 in range(0, nd, chunk_days):
+                d1 = min(nd, d0 + chunk_days)
+                for r in runs:
+                    sub = {k: (v[..., b0 + r[0]:b0 + r[-1] + 1] if isinstance(v, np.ndarray) else v) for k, v in shard_cells_np.items()}
+                    filler.fill(sub, d_chunk[0][:, r[0]:], d_chunk[1][:, r[0]:], d_chunk[2][:, r[0]:], day0=d0, n_days=d1 - d0)
+                for h, dsrc in zip(buf["f"], d_chunk):
+                    h[d0:d1, :n].copy_(dsrc[:d1 - d0, :n])
             for k, v in buf["cells"].items():
                 v[..., :n] = shard_cells_np[k][..., b0:b1]
+            torch.cuda.synchronize()
             return n
 
-        def structs(buf, n):
+        def structs(n):
             hp = {k: v.ctypes.data for k, v in buf["cells"].items()}
             bin_ = grid_in_struct(n, nd, year, doy, month, buf["f"][0].data_ptr(), buf["f"][1].data_ptr(), buf["f"][2].data_ptr(), hp,
                                   _abi.SPLASH_MEM_HOST, f32=False)
@@ -588,64 +583,36 @@ def main():
             return bin_, bout
 
         n_e2e = min(max(1, args.steps), E2E_MAX_STEPS)
-        t_steps, restage_s = [], []
+        t_steps = np.zeros(n_e2e)
         h2d_b = d2h_b = 0
         block_stats = []
-        cl = Cluster([local_rank], lanes)
-
-        def one_pass():
-            """All blocks of the shard through the scheduler with a rolling window of n_buf pinned buffers: a finished
-            block's buffer is refilled with the next block (that refill -- the caller reading its next block -- runs inside
-            the timed region when there are more blocks than buffers) and submitted.  Precondition: blocks 0..n_buf-1 staged."""
-            nonlocal h2d_b, d2h_b
-            stats, t_restage = [], 0.0
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            owner = {}
-            for i in range(n_buf):
-                owner[cl.submit(*_io[i])] = i
-            nxt = n_buf
-            while owner:
-                tk, s = cl.wait(-1)
-                i = owner.pop(tk)
-                stats.append(s)
-                if nxt < n_blocks:
-                    tr = time.perf_counter()
-                    bi, bo = structs(bufs[i], stage(nxt, bufs[i]))
-                    t_restage += time.perf_counter() - tr
-                    _io[i] = (bi, hopts, bo)
-                    owner[cl.submit(bi, hopts, bo)] = i
-                    nxt += 1
-            return time.perf_counter() - t, stats, t_restage
-
-        _io = [None] * n_buf
         barrier()  # the ranks start their host-fed passes together (they share the host's memory and PCIe fabric)
-        for rep in range(1 + n_e2e):   # one untimed pass sizes the lanes' device buffers
-            for i in range(n_buf):     # (re)stage the first blocks: untimed, the caller's data
-                bi, bo = structs(bufs[i], stage(i, bufs[i]))
-                _io[i] = (bi, hopts, bo)
-            dt, stats, t_rs = one_pass()
-            if rep:
-                t_steps.append(dt)
-                restage_s.append(t_rs)
-                launches += sum(s["kernel_launches"] for s in stats)
-            if rep == n_e2e:
-                h2d_b, d2h_b = sum(s["h2d_bytes"] for s in stats), sum(s["d2h_bytes"] for s in stats)
-                block_stats = [{q: s[q] for q in ("total_ms", "gpu_ms", "h2d_ms", "d2h_ms", "pool_wait_ms", "first_ms", "rounds_ms",
-                                                  "bulk_ms", "n_tiles", "tile_cells", "pool_cells", "pool_max_passes")} for s in stats]
-        cl.close()
-        t_e2e = allreduce(float(np.mean(t_steps)), "max")
+        for b in range(n_blocks):
+            bin_, bout = structs(stage(b))
+            for rep in range((1 if b == 0 else 0) + n_e2e):   # one untimed call of the first block sizes the device buffers
+                k = rep - (1 if b == 0 else 0)
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                ctx.grid_run(bin_, hopts, bout)
+                dt = time.perf_counter() - t
+                if k >= 0:
+                    t_steps[k] += dt
+                    s_ = ctx.stats()
+                    launches += s_["kernel_launches"]
+                    if k == n_e2e - 1:
+                        h2d_b += s_["h2d_bytes"]
+                        d2h_b += s_["d2h_bytes"]
+                        block_stats.append({q: s_[q] for q in ("total_ms", "gpu_ms", "h2d_ms", "d2h_ms", "pool_wait_ms", "first_ms", "rounds_ms",
+                                                               "bulk_ms", "n_tiles", "tile_cells", "pool_cells", "pool_max_passes")})
+        t_e2e = allreduce(float(t_steps.mean()), "max")
         e2e = {"value": job_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
-               "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "row_blocks": n_blocks, "pinned_block_buffers": n_buf, "lanes": lanes,
-               "caller_refill_s_inside_timed_region": float(np.mean(restage_s)),
-               "host_buffers": "pinned f64 (what R's REAL() holds), day-major; blocks go through splash_cluster_submit / _wait (the "
-                               "reference's sendCall / recvOneData) with a rolling window of pinned buffers; refilling a buffer with "
-                               "the caller's next block happens inside the timed region",
+               "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "row_blocks": n_blocks,
+               "host_buffers": "pinned f64 (what R's REAL() holds), day-major; one block of rows per call (splash_grid_run on host "
+                               "pointers), each block staged once and run for every timed pass",
                "block_stats_last_step": block_stats}
-        del bufs, d_chunk
+        del bufs, buf, d_chunk
         torch.cuda.empty_cache()
         phases["e2e_s"] = time.perf_counter() - t0
-        ctx = Context(local_rank)
 
     # ---- weak-scaling figure beside the strong one (N > 1): one whole grid per rank ------------------------
     weak_value = None

@@ -292,6 +292,37 @@ typedef struct splash_m2d_in {
 /* daily_out: [n_days*out_stride] double or float according to in->out_f32. */
 int splash_month2day_linear(splash_ctx* ctx, const splash_m2d_in* in, void* daily_out);
 
+/* ---- terrain preprocessing, first slice: what splash.grid derives from the DEM before the hot path ----
+ * Small-grid branch of splash.grid (R/splash.grid.R:95-110): resolution <- sqrt(area(elev)) * 1000, lat from the cell
+ * centres, terrain(elev, opt = c('slope', 'aspect'), unit = 'degrees') with NA slopes of valid cells set to 0 (:107), and
+ * of upslope_area() (R/upslope_area.R:12-58) the flow direction terrain(elev, opt = 'flowdir') and the in-tree focal
+ * counts ncellflow(flowdir, 'in' | 'out', met = 'top') (:140-165).  The contributing area itself comes from
+ * topmodel::sinkfill / topidx (CRAN, not in the reference tree) and stays with the caller.
+ * PARITY UNPINNED: raster::terrain and raster::area are third-party code that is not in /root/reference; the kernels
+ * follow their published formulas (Horn 1981 slope/aspect on 8 neighbours with metric cell sizes from the latitude,
+ * D8 flow direction with codes 1 = E, 2 = SE, 4 = S, ... 128 = NE, drop over distance), and where raster is random (ties
+ * of the steepest drop) the lowest code wins. */
+typedef struct splash_terrain_in {
+    int64_t n_rows, n_cols;
+    const double* elev;     /* [n_rows*n_cols] row-major, north row first (raster order); NaN = NA */
+    double ymax;            /* northern edge of the grid (degrees, or metres when lonlat == 0) */
+    double xres, yres;      /* cell size (degrees, or metres when lonlat == 0) */
+    int32_t lonlat;         /* 1: geographic coordinates (cell sizes in metres follow from the latitude) */
+    int32_t mem_kind;       /* SPLASH_MEM_HOST or SPLASH_MEM_DEVICE, inputs and outputs alike */
+} splash_terrain_in;
+
+typedef struct splash_terrain_out {  /* every layer [n_rows*n_cols] row-major; any pointer may be NULL */
+    double* slope;          /* degrees; NA (border / NA neighbour) of a valid cell -> 0, R/splash.grid.R:107 */
+    double* aspect;         /* degrees clockwise from north; same NA rule */
+    double* lat;            /* latitude of the cell centre where elev is valid, else NA (:101-104) */
+    double* resolution;     /* sqrt(cell area) in m (:98) */
+    double* flowdir;        /* D8 code, NA on the border and where a neighbour is NA */
+    double* ncellin;        /* cells draining in, at least 1 (ncellflow's nmatch[nmatch==0] <- 1); NA where all nine flowdir are NA */
+    double* ncellout;       /* ncellflow(flowdir, 'out', 'top') */
+} splash_terrain_out;
+
+int splash_terrain_run(splash_ctx* ctx, const splash_terrain_in* in, splash_terrain_out* out);
+
 /* Diagnostic (used by tests/test_math_gpu.py, not by the R glue): apply one of the day step's
  * transcendental functions to a host array on the device.  op: 0 exp, 1 log, 2 acos, 3 sin (hour
  * angles, [0, pi]).  These are the library's own implementations (csrc/splash_math.cuh), which stand

@@ -114,6 +114,17 @@ class SplashM2dIn(C.Structure):
     ]
 
 
+class SplashTerrainIn(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_int64), ("n_cols", C.c_int64), ("elev", C.c_void_p), ("ymax", C.c_double), ("xres", C.c_double),
+        ("yres", C.c_double), ("lonlat", C.c_int32), ("mem_kind", C.c_int32),
+    ]
+
+
+class SplashTerrainOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("slope", "aspect", "lat", "resolution", "flowdir", "ncellin", "ncellout")]
+
+
 class SplashStats(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_double),

@@ -190,6 +190,26 @@ def unSWC_grid(soil_data, uns_depth: float, wn, ctx: Context | None = None) -> d
     return res
 
 
+def terrain(elev, ymax: float, xres: float, yres: float, lonlat: bool = True, ctx: Context | None = None) -> dict:
+    """What splash.grid derives from the DEM before the hot path (R/splash.grid.R:95-110, R/upslope_area.R:27-29,
+    140-165): slope and aspect (degrees, NA of valid cells -> 0), latitude, resolution = sqrt(cell area) in m, D8 flow
+    direction and the cells draining in / out.  elev: [n_rows, n_cols], north row first.  Parity unpinned (raster::terrain
+    and raster::area are third-party; see include/splash_cuda.h)."""
+    ctx = ctx or default_context()
+    z = np.ascontiguousarray(elev, dtype=np.float64)
+    if z.ndim != 2:
+        raise ValueError("elev must be [n_rows, n_cols]")
+    cin = _abi.SplashTerrainIn()
+    cin.n_rows, cin.n_cols, cin.elev = z.shape[0], z.shape[1], _ptr(z)
+    cin.ymax, cin.xres, cin.yres, cin.lonlat, cin.mem_kind = float(ymax), float(xres), float(yres), int(bool(lonlat)), _abi.SPLASH_MEM_HOST
+    res = {k: np.empty(z.shape) for k in ("slope", "aspect", "lat", "resolution", "flowdir", "ncellin", "ncellout")}
+    cout = _abi.SplashTerrainOut()
+    for k, v in res.items():
+        setattr(cout, k, _ptr(v))
+    ctx.check(ctx.lib.splash_terrain_run(ctx.handle, C.byref(cin), C.byref(cout)))
+    return res
+
+
 def month_starts(time_index_month, time_index) -> np.ndarray:
     """0-based position on the daily axis of each month's first day (time_index_month - time_index[1])."""
     tm = np.asarray(time_index_month, dtype="datetime64[D]")

@@ -83,6 +83,19 @@ constexpr int kUBlocks = SPLASH_UBLOCKS;
 #define SPLASH_UREG_SLACK 64
 #endif
 constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
+// SPLASH_UREGS: the register cap of the uniform kernels.  A full 512-thread CTA at 104 registers leaves 12 288 registers
+// of its SM free: three one-warp CTAs of the straggler pool (128 registers per thread).  Measured on the resident
+// benchmark (profiles/README.md): 96 registers (what a launch bound of 576 threads gives) 3.09 s per pass, 104: 2.92 s,
+// 112 / 120 / 128: faster bulk kernel alone (up to +15 %) but 3.1 - 3.9 s per pass, because pool warps and such CTAs then
+// exclude each other from an SM and the straggler chain ends after the bulk launches.  SPLASH_UREGS=0: launch bound.
+#ifndef SPLASH_UREGS
+#define SPLASH_UREGS 104
+#endif
+#if SPLASH_UREGS > 0
+#define SPLASH_UNIFORM_BOUNDS __maxnreg__(SPLASH_UREGS)
+#else
+#define SPLASH_UNIFORM_BOUNDS __launch_bounds__(kUBound, kUBlocks)
+#endif
 constexpr int kSpinYear = 365; // R/splash.point.R:141-152: the spin-up year is always 365 days
 
 __constant__ MonthTab c_month_tab;
@@ -379,7 +392,7 @@ __device__ __forceinline__ bool spin_decide(const CellState& Ek, double chk_wn, 
 
 // ---- K2a: aridity pass + pass 0 of the second spin_up, all cells, 730 uniform days ---------------
 template <typename FT>
-__global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_first(RunParams p) {
+__global__ void SPLASH_UNIFORM_BOUNDS k_spin_first(RunParams p) {
     extern __shared__ double s_cc[];
     const int c = blockIdx.x * kUThreads + threadIdx.x;
     const bool live = c < p.n_cells;  // threads past the tile's end idle through the loop: every thread reaches every barrier
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_spin_check(RunParams p
 
 // ---- K2c: days 2..365 of a year pass for the (compacted) cells that continue ----------------------
 template <typename FT>
-__global__ void __launch_bounds__(kUBound, kUBlocks) k_spin_rest(RunParams p) {
+__global__ void SPLASH_UNIFORM_BOUNDS k_spin_rest(RunParams p) {
     extern __shared__ double s_cc[];
     const int r = p.round;
     const unsigned long long i = (unsigned long long)blockIdx.x * kUThreads + threadIdx.x;
@@ -556,10 +569,10 @@ __device__ __forceinline__ void emit_day(const RunParams& p, int c, int d, const
 // uniform day loop (every live thread of the CTA runs days 0..n_days-1; the CTA meets at a barrier per day).
 // Thread i integrates cell p.order[i] (i < ctl->n_ready): the tile's cells regime-sorted by k_regime_*, so that
 // the cells of a warp take the same branches of the day step more often (flat / sloped, deep / shallow soil,
-// frost and snow frequency, aridity); without an order, cell i.  The next day's forcing is loaded before the
-// current day is computed, so that the (scattered, L2-resident) loads are off the dependent path.
+// frost and snow frequency, aridity); without an order (the default: the sort was measured slower on the synthetic grid,
+// whose divergence is day-to-day weather, not regime), cell i.
 template <typename FT, bool kMonthly>
-__global__ void __launch_bounds__(kUBound, kUBlocks) k_run_bulk(RunParams p) {
+__global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
     extern __shared__ double s_cc[];
     StridedCC cc{s_cc + threadIdx.x, kUThreads};
     const long long i0 = (long long)blockIdx.x * kUThreads;
@@ -587,32 +600,13 @@ __global__ void __launch_bounds__(kUBound, kUBlocks) k_run_bulk(RunParams p) {
     int n_snowfall = 0;
     MonthAcc macc;
     macc.clear();
-    double n_sw = 0.0, n_tc = 0.0, n_pn = 0.0;  // forcing of the next day
-    if (live && p.n_days > 0) {
-        n_sw = ld_stream(sw_col);
-        n_tc = ld_stream(tc_col);
-        n_pn = ld_stream(pn_col);
-    }
     for (int d = 0; d < p.n_days; ++d) {
-#ifdef SPLASH_NO_PREFETCH
         double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
-        if (live) {
-            f_sw = ld_stream(sw_col + (int64_t)d * p.fpitch);
+        if (live) {  // (loading the next day's forcing one day ahead was measured: no gain, three more live registers)
+            const int64_t off = (int64_t)d * p.fpitch;
+            f_sw = ld_stream(sw_col + off);
             f_tc = ld_stream(tc_col + (int64_t)d * p.tpitch);
-            f_pn = ld_stream(pn_col + (int64_t)d * p.fpitch);
-        }
-#else
-        const double f_sw = n_sw, f_tc = n_tc, f_pn = n_pn;
-#endif
-#ifdef SPLASH_NO_PREFETCH
-        if (false) {
-#else
-        if (live && d + 1 < p.n_days) {
-#endif
-            const int64_t off = (int64_t)(d + 1) * p.fpitch;
-            n_sw = ld_stream(sw_col + off);
-            n_tc = ld_stream(tc_col + (int64_t)(d + 1) * p.tpitch);
-            n_pn = ld_stream(pn_col + off);
+            f_pn = ld_stream(pn_col + off);
         }
         const DayTab dt = p.dtab[d];
         if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
@@ -1115,6 +1109,108 @@ __global__ void __launch_bounds__(256) k_unswc(UnswcParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Terrain preprocessing, first slice (see include/splash_cuda.h: PARITY UNPINNED, raster::terrain /
+// raster::area are not in the reference tree).  One thread per cell, a 3x3 stencil over the DEM: an HBM-bound map
+// (8 B read + <= 40 B written per cell; the eight neighbour reads hit L1/L2).
+// ---------------------------------------------------------------------------------------------
+struct TerrainParams {
+    const double* elev;
+    double *slope, *aspect, *lat, *resolution, *flowdir, *ncellin, *ncellout;
+    int64_t n_rows, n_cols;
+    double ymax, xres, yres;
+    int lonlat;
+};
+
+constexpr double kEarthR = 6378137.0;  // raster's default sphere for lon/lat distances
+
+__device__ __forceinline__ void terrain_cell_size(const TerrainParams& p, int64_t r, double& dx, double& dy, double& lat_c) {
+    lat_c = p.ymax - ((double)r + 0.5) * p.yres;
+    if (p.lonlat) {
+        dy = kEarthR * (p.yres * kpir);
+        dx = kEarthR * cos(lat_c * kpir) * (p.xres * kpir);
+    } else {
+        dy = p.yres;
+        dx = p.xres;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_terrain(TerrainParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_rows * p.n_cols) return;
+    const int64_t r = i / p.n_cols, c = i - r * p.n_cols;
+    const double z0 = p.elev[i];
+    double dx, dy, lat_c;
+    terrain_cell_size(p, r, dx, dy, lat_c);
+    const bool valid = !isnan(z0);
+    if (p.lat) p.lat[i] = valid ? lat_c : nan("");                       // lat <- elev * 0; lat[!is.na(lat)] <- y
+    if (p.resolution) p.resolution[i] = sqrt(dx * dy);                   // sqrt(area km2) * 1000
+    double slope = nan(""), aspect = nan(""), fd = nan("");
+    if (r > 0 && r + 1 < p.n_rows && c > 0 && c + 1 < p.n_cols) {
+        const double* e = p.elev + i;
+        const int64_t nc = p.n_cols;
+        const double z1 = e[-nc - 1], z2 = e[-nc], z3 = e[-nc + 1], z4 = e[-1], z6 = e[1], z7 = e[nc - 1], z8 = e[nc], z9 = e[nc + 1];
+        const bool all_ok = valid && !(isnan(z1) || isnan(z2) || isnan(z3) || isnan(z4) || isnan(z6) || isnan(z7) || isnan(z8) || isnan(z9));
+        if (all_ok) {
+            // Horn (1981), 8 neighbours: east-minus-west and north-minus-south gradients
+            const double zx = ((z3 + 2.0 * z6 + z9) - (z1 + 2.0 * z4 + z7)) / (8.0 * dx);
+            const double zy = ((z1 + 2.0 * z2 + z3) - (z7 + 2.0 * z8 + z9)) / (8.0 * dy);
+            slope = atan(sqrt(zx * zx + zy * zy)) / kpir;
+            // downslope direction clockwise from north; flat cells: 90 degrees (the model multiplies it by sin(slope) = 0)
+            double a = (kPI / 2.0 - atan2(-zy, -zx)) / kpir;
+            if (a < 0.0) a += 360.0;
+            if (a >= 360.0) a -= 360.0;
+            if (zx == 0.0 && zy == 0.0) a = 90.0;
+            aspect = a;
+            // D8: steepest drop over distance; codes 1 E, 2 SE, 4 S, 8 SW, 16 W, 32 NW, 64 N, 128 NE; ties: lowest code
+            const double dd = sqrt(dx * dx + dy * dy);
+            const double drop[8] = {(z0 - z6) / dx, (z0 - z9) / dd, (z0 - z8) / dy, (z0 - z7) / dd,
+                                    (z0 - z4) / dx, (z0 - z1) / dd, (z0 - z2) / dy, (z0 - z3) / dd};
+            int best = 0;
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                if (drop[k] > drop[best]) best = k;
+            fd = (double)(1 << best);
+        }
+    }
+    if (valid && isnan(slope)) slope = 0.0;    // terraines[is.na(terraines) & !is.na(elev)] <- 0, R/splash.grid.R:107
+    if (valid && isnan(aspect)) aspect = 0.0;
+    if (p.slope) p.slope[i] = slope;
+    if (p.aspect) p.aspect[i] = aspect;
+    if (p.flowdir) p.flowdir[i] = fd;
+}
+
+// ncellflow(flowdir, inout, met = 'top'), R/upslope_area.R:140-165: focal 3x3 count of the neighbours whose direction
+// equals the template (column-major fill of matrix(c(2,1,128,4,0,64,8,16,32), nrow = 3): NW 2, W 1, SW 128, N 4, S 64,
+// NE 8, E 16, SE 32 -- each neighbour pointing at the centre; 'out' uses the reversed vector), zero matches -> 1, and NA
+// where all nine values are NA.  Cells outside the grid count as NA (raster::focal pads with NA).
+__global__ void __launch_bounds__(256) k_ncellflow(TerrainParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_rows * p.n_cols) return;
+    const int64_t r = i / p.n_cols, c = i - r * p.n_cols;
+    // window in raster::focal's order read column by column to match the column-major template
+    const int dr[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+    const int dc[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1};
+    const double t_in[9] = {2, 1, 128, 4, 0, 64, 8, 16, 32};
+    int n_na = 0, m_in = 0, m_out = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int64_t rr = r + dr[k], cc2 = c + dc[k];
+        double v = nan("");
+        if (rr >= 0 && rr < p.n_rows && cc2 >= 0 && cc2 < p.n_cols) v = p.flowdir[rr * p.n_cols + cc2];
+        if (isnan(v)) {
+            ++n_na;
+        } else {
+            m_in += (v == t_in[k]) ? 1 : 0;
+            m_out += (v == t_in[8 - k]) ? 1 : 0;
+        }
+    }
+    const double vin = (n_na == 9) ? nan("") : (double)(m_in == 0 ? 1 : m_in);
+    const double vout = (n_na == 9) ? nan("") : (double)(m_out == 0 ? 1 : m_out);
+    if (p.ncellin) p.ncellin[i] = vin;
+    if (p.ncellout) p.ncellout[i] = vout;
+}
+
 // diagnostic: the day step's transcendental functions applied to an array (splash_debug_math)
 __global__ void k_debug_math(int op, int64_t n, const double* x, double* y) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1592,8 +1688,13 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    for (auto& s : ctx->s_run) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_lo));
-    for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));  // stragglers first
+    // Stragglers first (the chain of the slowest cell is the critical path of a call), then the tiles in order: tile t's
+    // stream outranks tile t+1's, so that the first tiles finish their spin-up -- and start their stragglers' chains --
+    // as early as possible instead of all tiles advancing abreast (numerically lower = higher priority).
+    const bool tile_prio = !getenv("SPLASH_TILE_PRIO") || atoi(getenv("SPLASH_TILE_PRIO")) != 0;  // (0: all tiles abreast)
+    for (int i = 0; i < kRunStreams; ++i)
+        CU(cudaStreamCreateWithPriority(&ctx->s_run[i], cudaStreamNonBlocking, tile_prio ? std::min(prio_lo, prio_hi + 1 + i) : prio_lo));
+    for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
     k_init_tables<<<(kSnowAgeTab + 255) / 256, 256>>>();
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -1748,6 +1849,62 @@ int splash_unswc_grid_run(splash_ctx* ctx, const splash_unswc_in* in, splash_uns
         if (cudaStreamSynchronize(S) != cudaSuccess) rc = SPLASH_ERR_CUDA;
     }
     if (rc != SPLASH_OK) return fail(ctx, rc, "splash_unswc_grid_run: %s", cudaGetErrorString(cudaGetLastError()));
+    return SPLASH_OK;
+}
+
+int splash_terrain_run(splash_ctx* ctx, const splash_terrain_in* in, splash_terrain_out* out) {
+    if (ctx && ctx->multi) {  // single-GPU work: the context's first lane does it
+        splash_ctx* lane = first_lane(ctx);
+        const int rc = splash_terrain_run(lane, in, out);
+        ctx->err = lane->err;
+        return rc;
+    }
+    if (!ctx) return SPLASH_ERR_BAD_ARG;
+    ctx->err.clear();
+    if (!in || !out) return fail(ctx, SPLASH_ERR_BAD_ARG, "splash_terrain_run: NULL in/out");
+    const int64_t nr = in->n_rows, ncol = in->n_cols;
+    if (nr < 0 || ncol < 0 || nr > (int64_t)1 << 31 || ncol > (int64_t)1 << 31) return fail(ctx, SPLASH_ERR_BAD_ARG, "bad n_rows/n_cols");
+    if (in->mem_kind != SPLASH_MEM_HOST && in->mem_kind != SPLASH_MEM_DEVICE)
+        return fail(ctx, SPLASH_ERR_BAD_ARG, "mem_kind must be SPLASH_MEM_HOST or SPLASH_MEM_DEVICE");
+    if (!(in->xres > 0) || !(in->yres > 0)) return fail(ctx, SPLASH_ERR_BAD_ARG, "xres and yres must be positive");
+    const int64_t n = nr * ncol;
+    if (n == 0) return SPLASH_OK;
+    if (!in->elev) return fail(ctx, SPLASH_ERR_BAD_ARG, "NULL elev");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t S = ctx->s_run[0];
+    double* const optr[7] = {out->slope, out->aspect, out->lat, out->resolution, out->flowdir, out->ncellin, out->ncellout};
+    TerrainParams p{};
+    p.n_rows = nr;
+    p.n_cols = ncol;
+    p.ymax = in->ymax;
+    p.xres = in->xres;
+    p.yres = in->yres;
+    p.lonlat = in->lonlat;
+    const bool need_fd = out->flowdir || out->ncellin || out->ncellout;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    TmpDev t_elev, t_out, t_fd;  // freed on every return path
+    double** slot[7] = {&p.slope, &p.aspect, &p.lat, &p.resolution, &p.flowdir, &p.ncellin, &p.ncellout};
+    if (in->mem_kind == SPLASH_MEM_DEVICE) {
+        p.elev = in->elev;
+        for (int k = 0; k < 7; ++k) *slot[k] = optr[k];
+        if (need_fd && !p.flowdir) {
+            CU(cudaMalloc(&t_fd.p, (size_t)n * 8));
+            p.flowdir = (double*)t_fd.p;
+        }
+    } else {
+        CU(cudaMalloc(&t_elev.p, (size_t)n * 8));
+        CU(cudaMalloc(&t_out.p, (size_t)n * 8 * 7));
+        CU(cudaMemcpyAsync(t_elev.p, in->elev, (size_t)n * 8, cudaMemcpyHostToDevice, S));
+        p.elev = (const double*)t_elev.p;
+        for (int k = 0; k < 7; ++k) *slot[k] = (optr[k] || (k == 4 && need_fd)) ? (double*)t_out.p + (size_t)k * n : nullptr;
+    }
+    k_terrain<<<grid, 256, 0, S>>>(p);
+    if (out->ncellin || out->ncellout) k_ncellflow<<<grid, 256, 0, S>>>(p);
+    CU(cudaGetLastError());
+    if (in->mem_kind == SPLASH_MEM_HOST)
+        for (int k = 0; k < 7; ++k)
+            if (optr[k]) CU(cudaMemcpyAsync(optr[k], *slot[k], (size_t)n * 8, cudaMemcpyDeviceToHost, S));
+    CU(cudaStreamSynchronize(S));
     return SPLASH_OK;
 }
 

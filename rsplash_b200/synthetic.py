@@ -181,10 +181,20 @@ class Grid:
     return the attributes / forcing of any subset; `tables()` are the host-built lookup tables both the numpy
     and the CUDA generator read."""
 
-    def __init__(self, n_cells: int = N_CELLS_5ARCMIN, seed: int = 20240, flat_fraction: float = 0.5):
-        self.n_cells, self.seed, self.flat_fraction = int(n_cells), int(seed), float(flat_fraction)
-        self.rows_n = land_cells_per_row(self.n_cells)
-        self.row_lat = row_latitudes()
+    def __init__(self, n_cells: int = N_CELLS_5ARCMIN, seed: int = 20240, flat_fraction: float = 0.5, shape=None,
+                 lat_range=(60.0, 24.0), cell_m: float | None = None):
+        """shape = (rows, cols): a fully-land rectangular grid between the two latitudes instead of the 5' global land mask
+        (BASELINE configs[4]: the 1-km continental grid, cell_m = 1000)."""
+        self.seed, self.flat_fraction, self.cell_m = int(seed), float(flat_fraction), cell_m
+        if shape is None:
+            self.n_cells = int(n_cells)
+            self.rows_n = land_cells_per_row(self.n_cells)
+            self.row_lat = row_latitudes()
+        else:
+            rows, cols = int(shape[0]), int(shape[1])
+            self.n_cells = rows * cols
+            self.rows_n = np.full(rows, cols, dtype=np.int64)
+            self.row_lat = lat_range[0] + (lat_range[1] - lat_range[0]) * (np.arange(rows) + 0.5) / rows
         self.row_start = np.concatenate([[0], np.cumsum(self.rows_n)])
 
     # ---- per-cell attributes (host, numpy; any libm call is fine here: computed once per process) ----
@@ -207,7 +217,10 @@ class Grid:
         gravel = 40.0 * u(23)
         bd = np.where(u(25) < 0.1, np.nan, 1.0 + 0.7 * u(24))
         depth = 0.3 + 2.7 * u(26)
-        res = f32(np.sqrt((111320.0 / 12.0) ** 2 * np.maximum(np.cos(np.deg2rad(lat)), 0.02)))
+        if self.cell_m is None:  # sqrt(area) of a 5' cell, m (R/splash.grid.R:98)
+            res = f32(np.sqrt((111320.0 / 12.0) ** 2 * np.maximum(np.cos(np.deg2rad(lat)), 0.02)))
+        else:
+            res = np.full(len(idx), float(self.cell_m))
         au = f32(res * res * (1.0 + np.exp(8.0 * u(27))))
         cellin = np.floor(1.0 + 8.0 * u(28) * 0.999999)
         cellout = np.floor(1.0 + 8.0 * u(29) * 0.999999)
@@ -221,7 +234,7 @@ class Grid:
         doy = np.asarray(doy, dtype=np.int32)
         season = 12.0 * np.cos(2.0 * np.pi * (doy.astype(np.float64) - 200.0) / 365.0)
         dd = np.arange(1, DOYS + 1, dtype=np.float64)[None, :]
-        phi = np.deg2rad(self.row_lat.astype(np.float32).astype(np.float64))[:, None]
+        phi = np.deg2rad(np.asarray(self.row_lat).astype(np.float32).astype(np.float64))[:, None]
         dr = 1.0 + 0.033 * np.cos(2.0 * np.pi * dd / 365.0)
         dec = 0.409 * np.sin(2.0 * np.pi * dd / 365.0 - 1.39)
         ws = np.arccos(np.clip(-np.tan(phi) * np.tan(dec), -1.0, 1.0))

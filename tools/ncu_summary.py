@@ -28,7 +28,7 @@ keep = [
     "smsp__sass_average_branch_targets_threads_uniform.pct",
 ] + sorted(k for k in d if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio"))
 with open(os.path.join(ROOT, "profiles", f"{tag}_bulk_metrics.txt"), "w") as out:
-    out.write(f"# ncu --set full --clock-control none, k_splash_fused<bulk>, {cells} cells x {days} days (tools/profile_case.py bulk)\n")
+    out.write(f"# ncu --set full --clock-control none, k_run_bulk<bulk>, {cells} cells x {days} days (tools/profile_case.py bulk)\n")
     for k in keep:
         if k in d:
             out.write(f"{k}\t{d[k][1]}\t{d[k][0]}\n")
@@ -36,7 +36,7 @@ dfma, dmul, dadd = (f("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % o) f
 unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
 dram = f("dram__bytes_read.sum") * unit[d["dram__bytes_read.sum"][0]] + f("dram__bytes_write.sum") * unit[d["dram__bytes_write.sum"][0]]
 work = {
-    "source": f"ncu capture profiles/{tag}_bulk_metrics.txt ({cells} cells x {days} days, k_splash_fused<bulk>)",
+    "source": f"ncu capture profiles/{tag}_bulk_metrics.txt ({cells} cells x {days} days, k_run_bulk<bulk>)",
     "fp64_inst_per_cell_day": (dfma + dmul + dadd) / cd, "dfma_per_cell_day": dfma / cd, "dmul_per_cell_day": dmul / cd,
     "dadd_per_cell_day": dadd / cd, "flops_per_cell_day": (2 * dfma + dmul + dadd) / cd,
     "thread_inst_per_cell_day": f("smsp__thread_inst_executed.sum") / cd, "dram_bytes_per_cell_day": dram / cd,
