@@ -352,6 +352,39 @@ __device__ __forceinline__ void spin_forcing(const RunParams& p, int c, int d, d
     }
 }
 
+// Next-day forcing in flight: the uniform kernels load day d+1's three values RAW (still float / double as stored) before
+// they compute day d and convert them at the top of the next iteration, so that the HBM latency of the load hides behind
+// a whole day step (in capture r02 the first use of the freshly loaded forcing -- its float-to-double conversion right
+// after the day barrier -- held 12.7 % of all stall samples).  `spin`: rows of the spin-up year (sw1 / tc / pn1, NA-padded).
+template <typename FT>
+struct RawForcing {
+    FT sw, tc, pn;
+};
+
+template <typename FT>
+__device__ __forceinline__ RawForcing<FT> ld_raw_main(const RunParams& p, int c, int d) {
+    RawForcing<FT> r;
+    const int64_t off = (int64_t)d * p.fpitch + c;
+    r.sw = __ldcs((const FT*)p.sw + off);
+    r.tc = __ldcs((const FT*)p.tc + (int64_t)d * p.tpitch + c);
+    r.pn = __ldcs((const FT*)p.pn + off);
+    return r;
+}
+
+template <typename FT>
+__device__ __forceinline__ RawForcing<FT> ld_raw_spin(const RunParams& p, int c, int d) {
+    RawForcing<FT> r;
+    if (d < p.n_days) {
+        const int64_t off = (int64_t)d * p.f1pitch + c;
+        r.sw = __ldcs((const FT*)p.sw1 + off);
+        r.tc = __ldcs((const FT*)p.tc + (int64_t)d * p.tpitch + c);
+        r.pn = __ldcs((const FT*)p.pn1 + off);
+    } else {  // x[1:365] pads short series with NA, R/splash.point.R:141-144
+        r.sw = r.tc = r.pn = (FT)nan("");
+    }
+    return r;
+}
+
 // The loop condition of SPLASH::spin_up (SPLASH.cpp:1697) evaluated after the check day, plus exact
 // cycle detection.  `Ek` is the end-of-pass state the check day started from, `chk_wn` the check
 // day's soil moisture.  Returns true when another year pass has to run.
@@ -405,10 +438,13 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_spin_first(RunParams p) {
     CompSum sum_pet, sum_p;  // aridity index, R/splash.point.R:147-150
     double AI = nan("");
     double w1 = 0.0;
+    RawForcing<FT> nxt{};
+    if (live) nxt = ld_raw_spin<FT>(p, c, 0);
     for (int it = 0; it < 2 * kSpinYear; ++it) {
         const int d = (it < kSpinYear) ? it : it - kSpinYear;
-        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
-        if (live) spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
+        const RawForcing<FT> cur = nxt;
+        if (live && it + 1 < 2 * kSpinYear) nxt = ld_raw_spin<FT>(p, c, (d + 1 == kSpinYear) ? 0 : d + 1);
+        const double f_sw = (double)cur.sw, f_tc = (double)cur.tc, f_pn = (double)cur.pn;
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
@@ -502,9 +538,12 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_spin_rest(RunParams p) {
         load_cc(p, c, cc);
         st = load_state(p.w, c);
     }
+    RawForcing<FT> nxt{};
+    if (live) nxt = ld_raw_spin<FT>(p, c, 1);
     for (int d = 1; d < kSpinYear; ++d) {
-        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
-        if (live) spin_forcing<FT>(p, c, d, f_sw, f_tc, f_pn);
+        const RawForcing<FT> cur = nxt;
+        if (live && d + 1 < kSpinYear) nxt = ld_raw_spin<FT>(p, c, d + 1);
+        const double f_sw = (double)cur.sw, f_tc = (double)cur.tc, f_pn = (double)cur.pn;
         const DayTab dt = p.dtab_spin[d];
         DayOut o;
         double rain, snowfall;
@@ -586,9 +625,6 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
         SPLASH_CHECK(c >= 0 && c < p.n_cells && n_run <= (long long)p.n_cells, 104);
         live = p.w.status[c] == ST_READY_BULK;
     }
-    const FT* sw_col = (const FT*)p.sw + c;
-    const FT* tc_col = (const FT*)p.tc + c;
-    const FT* pn_col = (const FT*)p.pn + c;
     CellState st{};
     double RES = 0.0, wrr = 1.0;
     if (live) {
@@ -600,14 +636,12 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
     int n_snowfall = 0;
     MonthAcc macc;
     macc.clear();
+    RawForcing<FT> nxt{};
+    if (live && p.n_days > 0) nxt = ld_raw_main<FT>(p, c, 0);
     for (int d = 0; d < p.n_days; ++d) {
-        double f_sw = 0.0, f_tc = 0.0, f_pn = 0.0;
-        if (live) {  // (loading the next day's forcing one day ahead was measured: no gain, three more live registers)
-            const int64_t off = (int64_t)d * p.fpitch;
-            f_sw = ld_stream(sw_col + off);
-            f_tc = ld_stream(tc_col + (int64_t)d * p.tpitch);
-            f_pn = ld_stream(pn_col + off);
-        }
+        const RawForcing<FT> cur = nxt;
+        if (live && d + 1 < p.n_days) nxt = ld_raw_main<FT>(p, c, d + 1);
+        const double f_sw = (double)cur.sw, f_tc = (double)cur.tc, f_pn = (double)cur.pn;
         const DayTab dt = p.dtab[d];
         if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
         if (!live) continue;
@@ -1487,8 +1521,16 @@ constexpr int kPoolStreams = 16;  // streams of the straggler-pool launches: a t
 #define SPLASH_ROUNDS 20
 #endif
 constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before the leftovers go to the pool
-constexpr int kPoolStage1Passes = 8;    // pass budget of the pool's first spin-up stage
-constexpr int kPoolStage2Passes = 128;  // ... and of the second; the third runs to the reference's pass limit
+// Pass budgets of the pool's first two spin-up stages and the shape of the third, which runs to the reference's pass
+// limit on SMs of its own.  Two presets, chosen per call by its size (profiles/README.md R2.2):
+//   large calls (the straggler chain hides behind seconds of bulk work): 8 / 128 passes, 16 cells per last-stage warp on 48
+//     CTAs -- few SMs taken away from the uniform kernels (resident benchmark: 2.83 s per pass against 2.97 s);
+//   small calls (chain-bound: row blocks of host-fed runs, shards of a strong-scaling run): 4 / 32 passes, 8 cells per
+//     warp on 96 CTAs -- the long runners reach their uncontended SMs sooner and share their warp, hence every divergent
+//     branch of the day step, with fewer cells (583 200 cells x 2 years: 1.59 s against 1.83 s).
+constexpr int kPoolStage1Passes = 8, kPoolStage2Passes = 128, kPoolLastLanes = 16, kPoolLastCtas = 48;
+constexpr int kPoolStage1Small = 4, kPoolStage2Small = 32, kPoolLastLanesSmall = 8, kPoolLastCtasSmall = 96;
+constexpr double kPoolSmallCallCellDays = 5e9;  // n_cells * n_days below which a call counts as chain-bound
 static_assert(kRounds <= kMaxRounds, "kRounds");
 constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
 
@@ -1519,7 +1561,8 @@ struct splash_ctx {
     int pool_stage1 = kPoolStage1Passes;  // SPLASH_POOL_STAGE1 (0 = single stage)
     int pool_stage2 = kPoolStage2Passes;  // SPLASH_POOL_STAGE2
     int pool_excl_smem = 0;               // dynamic shared memory of a last-stage CTA (SPLASH_POOL_EXCL=0: no exclusivity)
-    int pool_last_lanes = 16, pool_last_ctas = 48;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
+    int pool_last_lanes = kPoolLastLanes, pool_last_ctas = kPoolLastCtas;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
+    bool pool_auto = true;                // none of the four was set in the environment: preset by call size
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
     int64_t pool_cap = 0;                 // SPLASH_POOL_CAP: force the pool capacity (tests of the overflow path)
@@ -1666,6 +1709,7 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("SPLASH_RUN_STREAMS")) ctx->n_run_streams = std::max(1, std::min(kRunStreams, atoi(v)));
+    ctx->pool_auto = !getenv("SPLASH_POOL_STAGE1") && !getenv("SPLASH_POOL_STAGE2") && !getenv("SPLASH_POOL_LANES") && !getenv("SPLASH_POOL_CTAS");
     if (const char* v = getenv("SPLASH_POOL_STAGE1")) ctx->pool_stage1 = std::max(0, atoi(v));
     if (const char* v = getenv("SPLASH_TWO_PASS")) ctx->two_pass = atoi(v) != 0;
     if (const char* v = getenv("SPLASH_POOL_STAGE2")) ctx->pool_stage2 = std::max(1, atoi(v));
@@ -1688,10 +1732,11 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    // Stragglers first (the chain of the slowest cell is the critical path of a call), then the tiles in order: tile t's
-    // stream outranks tile t+1's, so that the first tiles finish their spin-up -- and start their stragglers' chains --
-    // as early as possible instead of all tiles advancing abreast (numerically lower = higher priority).
-    const bool tile_prio = !getenv("SPLASH_TILE_PRIO") || atoi(getenv("SPLASH_TILE_PRIO")) != 0;  // (0: all tiles abreast)
+    // Stragglers first (the chain of the slowest cell is the critical path of a call); the tiles abreast.
+    // SPLASH_TILE_PRIO=1 ranks tile t's stream above tile t+1's (earlier chain starts for the first tiles): measured
+    // WORSE on the resident benchmark (4.0 - 4.5 s per pass against 2.9 s: the later tiles' spin-ups starve and their
+    // chains end after everything else), kept as a knob only.
+    const bool tile_prio = getenv("SPLASH_TILE_PRIO") && atoi(getenv("SPLASH_TILE_PRIO")) != 0;
     for (int i = 0; i < kRunStreams; ++i)
         CU(cudaStreamCreateWithPriority(&ctx->s_run[i], cudaStreamNonBlocking, tile_prio ? std::min(prio_lo, prio_hi + 1 + i) : prio_lo));
     for (auto& s : ctx->s_pool) CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
@@ -2537,11 +2582,14 @@ struct GridJob {
             // forcing half of the cyclic year once, the spin-up chain on the state half, then the daily integration
             k_pool_table<FT><<<(unsigned)(ctx->sm_count * 2), 128, 0, Q>>>(pp, pool);
             // stage budgets: a short first look, a long second one, then the cells that may run to the pass limit
-            const int b1 = ctx->pool_stage1 > 0 ? ctx->pool_stage1 : (1 << 30);
+            const bool small_call = ctx->pool_auto && (double)nc * (double)nd < kPoolSmallCallCellDays;
+            const int s1 = small_call ? kPoolStage1Small : ctx->pool_stage1, s2 = small_call ? kPoolStage2Small : ctx->pool_stage2;
+            const int lanes3 = small_call ? kPoolLastLanesSmall : ctx->pool_last_lanes, ctas3 = small_call ? kPoolLastCtasSmall : ctx->pool_last_ctas;
+            const int b1 = s1 > 0 ? s1 : (1 << 30);
             k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1, b1, 32);
             CU(cudaEventRecord(e.ps1, Q));
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, ctx->pool_stage2, 32);
-            k_pool_spin<<<(unsigned)ctx->pool_last_ctas, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, ctx->pool_last_lanes);
+            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, s2, 32);
+            k_pool_spin<<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, lanes3);
             CU(cudaEventRecord(e.ps2, Q));
             CU(cudaGetLastError());
             launches += 4;
