@@ -385,6 +385,59 @@ __device__ __forceinline__ RawForcing<FT> ld_raw_spin(const RunParams& p, int c,
     return r;
 }
 
+// f32 forcing of the bulk kernel: the same one-day-ahead pipeline through shared memory with cp.async (LDGSTS): every thread
+// copies its own three values of day d+1 into a two-slot ring behind the cell constants (2 x 3 x 512 x 4 B = 12 KB, which
+// fits beside the 208 KB of constants; the f64 ring would not) while day d computes, and waits for its own copy group at the
+// top of the next day -- no registers held across the day step, no barrier (a thread reads only what it copied itself).
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename FT>
+struct BulkForcing {  // generic: raw values in registers (f64 forcing)
+    RawForcing<FT> nxt{};
+    __device__ __forceinline__ void start(const RunParams& p, int c, bool live, void*) {
+        if (live && p.n_days > 0) nxt = ld_raw_main<FT>(p, c, 0);
+    }
+    __device__ __forceinline__ void next(const RunParams& p, int c, int d, bool live, double& f_sw, double& f_tc, double& f_pn) {
+        const RawForcing<FT> cur = nxt;
+        if (live && d + 1 < p.n_days) nxt = ld_raw_main<FT>(p, c, d + 1);
+        f_sw = (double)cur.sw;
+        f_tc = (double)cur.tc;
+        f_pn = (double)cur.pn;
+    }
+};
+
+template <>
+struct BulkForcing<float> {  // f32: cp.async ring in shared memory
+    float* ring = nullptr;   // [2][3][kUThreads], this thread's column
+    __device__ __forceinline__ void issue(const RunParams& p, int c, int d) {
+        float* slot = ring + (d & 1) * 3 * kUThreads;
+        const int64_t off = (int64_t)d * p.fpitch + c;
+        cp_async_f32(slot, (const float*)p.sw + off);
+        cp_async_f32(slot + kUThreads, (const float*)p.tc + (int64_t)d * p.tpitch + c);
+        cp_async_f32(slot + 2 * kUThreads, (const float*)p.pn + off);
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void start(const RunParams& p, int c, bool live, void* smem_after_cc) {
+        ring = (float*)smem_after_cc + threadIdx.x;
+        if (live && p.n_days > 0) issue(p, c, 0);
+    }
+    __device__ __forceinline__ void next(const RunParams& p, int c, int d, bool live, double& f_sw, double& f_tc, double& f_pn) {
+        f_sw = f_tc = f_pn = 0.0;
+        if (!live) return;
+        cp_async_wait_all();
+        const float* slot = ring + (d & 1) * 3 * kUThreads;
+        f_sw = (double)slot[0];
+        f_tc = (double)slot[kUThreads];
+        f_pn = (double)slot[2 * kUThreads];
+        if (d + 1 < p.n_days) issue(p, c, d + 1);
+    }
+};
+
 // The loop condition of SPLASH::spin_up (SPLASH.cpp:1697) evaluated after the check day, plus exact
 // cycle detection.  `Ek` is the end-of-pass state the check day started from, `chk_wn` the check
 // day's soil moisture.  Returns true when another year pass has to run.
@@ -636,12 +689,11 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
     int n_snowfall = 0;
     MonthAcc macc;
     macc.clear();
-    RawForcing<FT> nxt{};
-    if (live && p.n_days > 0) nxt = ld_raw_main<FT>(p, c, 0);
+    BulkForcing<FT> pipe;
+    pipe.start(p, c, live, s_cc + (size_t)NCC_DAY * kUThreads);
     for (int d = 0; d < p.n_days; ++d) {
-        const RawForcing<FT> cur = nxt;
-        if (live && d + 1 < p.n_days) nxt = ld_raw_main<FT>(p, c, d + 1);
-        const double f_sw = (double)cur.sw, f_tc = (double)cur.tc, f_pn = (double)cur.pn;
+        double f_sw, f_tc, f_pn;
+        pipe.next(p, c, d, live, f_sw, f_tc, f_pn);
         const DayTab dt = p.dtab[d];
         if (kSync >= 1 && (d & kSyncMask) == 0) __syncthreads();
         if (!live) continue;
@@ -1623,7 +1675,9 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kTh
 inline unsigned ugrid_for(int64_t n) { return (unsigned)((n + kUThreads - 1) / kUThreads); }
 
 constexpr size_t kSmemSpin = sizeof(double) * NCC_DAY * kThreads;             // k_spin_check
-constexpr size_t kSmemUniform = sizeof(double) * NCC_DAY * kUThreads;         // k_spin_first, k_spin_rest, bulk launch
+constexpr size_t kSmemUniform = sizeof(double) * NCC_DAY * kUThreads;         // k_spin_first, k_spin_rest, bulk launch (f64 forcing)
+constexpr size_t kSmemBulkF32 = kSmemUniform + sizeof(float) * 2 * 3 * kUThreads;  // bulk launch, f32 forcing: + the cp.async ring
+template <typename FT> constexpr size_t bulk_smem() { return sizeof(FT) == 4 ? kSmemBulkF32 : kSmemUniform; }
 constexpr size_t kSmemList = sizeof(double) * (NCC_DAY + 5) * kListThreads;  // list mode: + cycle snapshot
 
 template <typename FT>
@@ -1632,8 +1686,8 @@ cudaError_t prepare_kernels() {
     if ((e = cudaFuncSetAttribute(k_spin_first<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
     if ((e = cudaFuncSetAttribute(k_spin_check<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpin))) return e;
     if ((e = cudaFuncSetAttribute(k_spin_rest<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
-    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
-    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUniform))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem<FT>()))) return e;
+    if ((e = cudaFuncSetAttribute(k_run_bulk<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem<FT>()))) return e;
     if ((e = cudaFuncSetAttribute(k_run_list<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     if ((e = cudaFuncSetAttribute(k_run_list<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
@@ -1645,9 +1699,9 @@ template <typename FT>
 void launch_bulk(const RunParams& rp, bool monthly, cudaStream_t s) {
     if (rp.n_cells <= 0) return;
     if (monthly)
-        k_run_bulk<FT, true><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
+        k_run_bulk<FT, true><<<ugrid_for(rp.n_cells), kUThreads, bulk_smem<FT>(), s>>>(rp);
     else
-        k_run_bulk<FT, false><<<ugrid_for(rp.n_cells), kUThreads, kSmemUniform, s>>>(rp);
+        k_run_bulk<FT, false><<<ugrid_for(rp.n_cells), kUThreads, bulk_smem<FT>(), s>>>(rp);
 }
 
 // list-mode launch: `warps` one-warp CTAs whose lanes fetch cells from the queue in rp

@@ -19,7 +19,7 @@ namespace hostsolar {
 const double ke = 0.0167, keps = 23.44, komega = 283.0;
 const double kPIh = 3.141592653589793, kpirh = (3.141592653589793 / 180.0);
 
-int julian_day(int y, int m, int i) {  // SOLAR.cpp:352-374, float jd kept (SURVEY B-5)
+inline int julian_day(int y, int m, int i) {  // SOLAR.cpp:352-374, float jd kept (SURVEY B-5)
     if (m <= 2.0) {
         y -= 1.0;
         m += 12.0;
@@ -32,9 +32,9 @@ int julian_day(int y, int m, int i) {  // SOLAR.cpp:352-374, float jd kept (SURV
 
 // volatile reads keep the compiler from folding the libm calls at build time: the reference
 // evaluates them at run time on extern constants.
-volatile double v_e = ke, v_eps = keps, v_omega = komega;
+inline volatile double v_e = ke, v_eps = keps, v_omega = komega;  // (inline: one definition however many translation units include this)
 
-void day_entry(int n, int y, DayTab* out) {
+inline void day_entry(int n, int y, DayTab* out) {
     const double e = v_e, eps = v_eps, omega = v_omega;
     const int kN = (y == 0) ? 365 : julian_day((y + 1), 1, 1) - julian_day(y, 1, 1);
     // berger_tls, SOLAR.cpp:308-345

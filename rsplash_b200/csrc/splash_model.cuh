@@ -17,11 +17,16 @@
 //                     SPLASH::run_one_day (src/SPLASH.cpp:984-1583) incl. moist_surf (:1921-1961)
 //                     and inf_GA (:1963-2023)
 //
-// Numerics: the arithmetic follows the reference's expression shapes and evaluation order; the
-// file is compiled with -fmad=false (the reference build has no FMA contraction, SURVEY B-9).
-// Hoisting is limited to sub-expressions whose value is bit-identical when computed once
-// (same operands, same operation order).  Differences against the CPU reference therefore come
-// from libdevice vs glibc transcendentals only (<= 2 ulp each).
+// Numerics: the formulas and their order follow the reference; the file is compiled with -fmad=false
+// (the reference build has no FMA contraction, SURVEY B-9).  With -DSPLASH_LEVEL=0 every operation is the
+// reference's and hoisting is limited to sub-expressions that are bit-identical when computed once; the
+// differences against the CPU reference are then libdevice vs glibc transcendentals (<= 2 ulp each).
+// The DEFAULT, level 1, additionally evaluates x^y as exp(y log x) with shared logarithms, divides by
+// guarded reciprocal multiplication, uses the library's own exp/log/acos (<= 1.5 ulp) and reproduces five
+// floating-point accidents of the reference explicitly: a few tens of ulp per
+// operation, which only ill-conditioned cells turn into more than the gates
+// (profiles/r02_level_table.json: 91 cells of 12 000 against 22 at level 0 and 102 for the reference's own
+// -mfma build).
 #pragma once
 
 // SPLASH_LEVEL selects how literally the day step follows the reference's floating-point recipe:

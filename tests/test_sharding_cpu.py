@@ -35,10 +35,18 @@ import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, os.environ["REPO"])
 from rsplash_b200 import synthetic
+import bench
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-rows = synthetic.land_cells_per_row(100000)
-c0, c1 = synthetic.shard_rows(rows, world)[rank]
+# bench.py's strong-scaling deal: blocks of grid rows round-robin to the ranks (the reference's block scheduler)
+grid = synthetic.Grid(100000, bench.GRID_SEED)
+idx = bench.seg_index(bench.rank_cells(grid, world, rank, True))
+# every rank holds its own cells of the ONE grid: gather the index sets and check that they partition it
+parts = [None] * world
+dist.all_gather_object(parts, idx.tolist())
+allidx = np.sort(np.concatenate([np.asarray(p, dtype=np.int64) for p in parts]))
+assert np.array_equal(allidx, np.arange(100000)), "the ranks' cells do not partition the grid"
+c0, c1 = 0, len(idx)
 # the only cross-rank traffic of the path: job size (sum) and step time (max)
 job = torch.tensor([float((c1 - c0) * 3652)], dtype=torch.float64)
 t = torch.tensor([1.0 + rank], dtype=torch.float64)
