@@ -326,7 +326,10 @@ int splash_terrain_run(splash_ctx* ctx, const splash_terrain_in* in, splash_terr
 /* Diagnostic (used by tests/test_math_gpu.py, not by the R glue): apply one of the day step's
  * transcendental functions to a host array on the device.  op: 0 exp, 1 log, 2 acos, 3 sin (hour
  * angles, [0, pi]).  These are the library's own implementations (csrc/splash_math.cuh), which stand
- * in for the libm calls of src/SPLASH.cpp, src/EVAP.cpp and src/SOLAR.cpp. */
+ * in for the libm calls of src/SPLASH.cpp, src/EVAP.cpp and src/SOLAR.cpp.  op 4..10: the guard-free
+ * bodies of the branch-light day step and what they must equal bit for bit -- 4 acos body, 5 sqrt
+ * body, 6 sqrt, 7 division body, 8 division (second operand x[(7919 i + 13) mod n]), 9 exp body,
+ * 10 log body; NaN where an argument is outside the body's guard. */
 int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, double* y);
 
 #ifdef __cplusplus

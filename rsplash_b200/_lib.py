@@ -142,12 +142,14 @@ class Context:
                                              float(resolution), C.byref(opts), C.byref(cout)))
 
     def debug_math(self, op: str, x):
-        """exp / log / acos / sin of the day step evaluated on the device (diagnostic)."""
+        """exp / log / acos / sin of the day step evaluated on the device (diagnostic); the `*_body` ops are the
+        guard-free fast-range bodies of the branch-light day step (NaN outside their guards), `sqrt` / `div` the
+        compiler's own expansions they must equal (div: second operand x[(7919 i + 13) mod n])."""
         import numpy as np
 
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        self.check(self.lib.splash_debug_math(self.handle, ("exp", "log", "acos", "sin").index(op), x.size,
+        self.check(self.lib.splash_debug_math(self.handle, ("exp", "log", "acos", "sin", "acos_body", "sqrt_body", "sqrt", "div_body", "div", "exp_body", "log_body").index(op), x.size,
                                               x.ctypes.data_as(_abi.c_double_p), y.ctypes.data_as(_abi.c_double_p)))
         return y
 

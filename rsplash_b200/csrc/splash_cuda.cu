@@ -251,6 +251,7 @@ struct TileCtl {
     unsigned long long pool_head;            // work-fetch cursor of the pool's daily-integration launch
     unsigned long long spin_head;            // work-fetch cursor of the pool's first spin-up stage
     unsigned long long hard_n[4], hard_head[4];  // hard_n[s]: cells that exceeded stage s's pass budget; cursor of the stage that reads them
+    unsigned long long decl_n, decl_head;    // cells of the last stage that keep declining the branch-light day step (guarded route)
     unsigned long long tail_head, tail_end;  // leftovers that did not fit the pool: finished in the tile
     unsigned long long max_chain;            // most year passes executed by one thread of a list-mode launch
     unsigned long long n_ready;              // cells in the regime-sorted order of the bulk launch
@@ -970,6 +971,11 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
     }
 }
 
+constexpr int kFastDeclineLimit = 18;  // days of the probe pass (5 %) the branch-light route may decline before the cell goes to the guarded list
+// SPLASH_CHAIN_FAST: the chain's state half through the branch-light route (day_state_fast, splash_model.cuh)
+#ifndef SPLASH_CHAIN_FAST
+#define SPLASH_CHAIN_FAST 1
+#endif
 #ifdef SPLASH_CHAIN_SHARED_MATH
 using ChainMath = MathShared;
 #else
@@ -988,9 +994,24 @@ using ChainMath = MathInline;
 // while).  The last stage is launched with enough shared memory per CTA that no 512-thread CTA of the
 // uniform kernels fits beside it: its warps (at most four per SM) own their SM and run the chain at
 // its uncontended latency, roughly half the time per day step of a warp squeezed in beside 16 others.
-__global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget, int lanes) {
+//
+// kBoth (the last stage when SPLASH_CHAIN_FAST): the state half through day_state_fast (splash_model.cuh), which
+// shortens a lone warp's dependent chain by ~1.7x -- for the cells whose days stay inside its fast ranges.  A cell
+// that keeps declining it (a column at its residual moisture, a zero air-entry pressure ...) would pay for both
+// routes every day, and so would its warp.  So the last stage is two launches: a PROBE (stage 3) runs one year pass
+// of every cell on the fast route and sorts the cells into two lists by the number of days declined; the FINAL
+// launch (stage 4) gives its first `ctas_a` CTAs the fast route on the first list and the others the guarded route
+// on the second, fewer cells per warp.  (The interleaved chains want registers: 255 per thread, no spills; the
+// warps of these stages own their SM anyway.)
+constexpr int kStageProbe = 3, kStageFinal = 4;
+constexpr int kPoolDeclinerLanes = 2;  // cells per warp on the guarded route of the final launch (divergence is what it pays for)
+template <bool kBoth>
+__global__ void __launch_bounds__(kListThreads, kBoth ? 8 : 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget, int lanes,
+                                                                            int ctas_a, int lanes_b) {
     extern __shared__ double s_cc[];
-    if ((int)threadIdx.x >= lanes) return;  // last stage: fewer cells per warp = fewer divergent paths per day step
+    const bool role_b = kBoth && stage == kStageFinal && (int)blockIdx.x >= ctas_a;  // guarded route on the decliners
+    const bool fast = kBoth && !role_b;
+    if ((int)threadIdx.x >= (role_b ? lanes_b : lanes)) return;  // last stage: fewer cells per warp = fewer divergent paths per day step
     StridedCC cc{s_cc + threadIdx.x, kListThreads};
     StridedCC snap{s_cc + (int64_t)NCC_DAY * kListThreads + threadIdx.x, kListThreads};
     unsigned long long spin_days = 0;
@@ -1001,6 +1022,10 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
             const unsigned long long i = atomicAdd(&p.ctl->spin_head, 1ULL);
             if (i >= p.ctl->pool_end) break;
             c = (int)i;
+        } else if (role_b) {  // the decliners' list grows down from the end of the tile's range
+            const unsigned long long i = atomicAdd(&p.ctl->decl_head, 1ULL);
+            if (i >= p.ctl->decl_n) break;
+            c = pool.hard[(stage - 1) & 1][p.ctl->pool_end - 1 - i];
         } else {
             const unsigned long long i = atomicAdd(&p.ctl->hard_head[stage - 1], 1ULL);
             if (i >= p.ctl->hard_n[stage - 1]) break;
@@ -1017,6 +1042,7 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
         const double2* tab = reinterpret_cast<const double2*>(pool.table + (long long)c * kSpinYear * kDayPrePad);
         bool cont = true;
         int d = 0;
+        int declined = 0;  // days of this stage that day_state_fast handed to the guarded route
         while (cont) {
             DayPre pre;
             {
@@ -1035,7 +1061,11 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
             }
             if (d == 0) saved = st;  // E_k: state of day 365 before the check day
             DayOut o;
-            day_state<ChainMath>(cc, pre, st, o);
+            if constexpr (kBoth) {
+                declined += day_state_auto<ChainMath>(cc, pre, st, o, fast) ? 0 : 1;
+            } else {
+                day_state<ChainMath>(cc, pre, st, o);
+            }
             ++spin_days;
             if (d == 0) {
                 bool hit_limit, cycle_found;
@@ -1051,16 +1081,21 @@ __global__ void __launch_bounds__(kListThreads, 16) k_pool_spin(RunParams p, Poo
                 if (chain >= budget) break;  // st == E_k, the end of a pass: the next stage resumes from it
             }
         }
-        if (cont) {  // budget exhausted: park the cell for stage 2
+        if (cont) {  // budget exhausted: park the cell for the next stage
             store_state(p.w, c, st);
             p.w.w1[c] = w1;
             p.w.passes[c] = passes;
             p.w.snap_pass[c] = snap_pass;
 #pragma unroll
             for (int k = 0; k < 5; ++k) p.w.snap[(int64_t)k * p.w.pitch + c] = snap(k);
-            const unsigned long long k2 = atomicAdd(&p.ctl->hard_n[stage], 1ULL);
-            SPLASH_CHECK(p.ctl->pool_base + k2 < p.ctl->pool_end, 111);
-            pool.hard[stage & 1][p.ctl->pool_base + k2] = c;
+            if (kBoth && stage == kStageProbe && declined > kFastDeclineLimit) {
+                const unsigned long long k2 = atomicAdd(&p.ctl->decl_n, 1ULL);
+                pool.hard[stage & 1][p.ctl->pool_end - 1 - k2] = c;
+            } else {
+                const unsigned long long k2 = atomicAdd(&p.ctl->hard_n[stage], 1ULL);
+                SPLASH_CHECK(p.ctl->pool_base + k2 < p.ctl->pool_end, 111);
+                pool.hard[stage & 1][p.ctl->pool_base + k2] = c;
+            }
             continue;
         }
         store_state(p.w, c, saved);  // the day-365 state is handed over, not the check day's
@@ -1302,7 +1337,21 @@ __global__ void k_debug_math(int op, int64_t n, const double* x, double* y) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    y[i] = op == 0 ? f_exp(v) : op == 1 ? f_log(v) : op == 2 ? f_acos(v) : f_sin(v);
+    const double w = x[(i * 7919 + 13) % n];  // second operand of the division checks
+    switch (op) {
+        case 0: y[i] = f_exp(v); break;
+        case 1: y[i] = f_log(v); break;
+        case 2: y[i] = f_acos(v); break;
+        case 3: y[i] = f_sin(v); break;
+        // the branch-light bodies against what they stand for (bit for bit inside their guards, NaN outside)
+        case 4: y[i] = fm::acos_ok(v) ? fm::acos_body(v) : nan(""); break;
+        case 5: y[i] = fm::sqrt_ok(v) ? fm::sqrt_body(v) : nan(""); break;
+        case 6: y[i] = fm::sqrt_ok(v) ? sqrt(v) : nan(""); break;
+        case 7: y[i] = fm::div_ok(v, w) ? fm::div_body(v, w) : nan(""); break;
+        case 8: y[i] = fm::div_ok(v, w) ? v / w : nan(""); break;
+        case 9: y[i] = fm::exp_ok(v) ? fm::exp_body(v) : nan(""); break;
+        default: y[i] = fm::log_ok(v) ? fm::log_body(v) : nan(""); break;
+    }
 }
 
 __global__ void k_init_tables() {
@@ -1614,6 +1663,7 @@ struct splash_ctx {
     int pool_stage2 = kPoolStage2Passes;  // SPLASH_POOL_STAGE2
     int pool_excl_smem = 0;               // dynamic shared memory of a last-stage CTA (SPLASH_POOL_EXCL=0: no exclusivity)
     int pool_last_lanes = kPoolLastLanes, pool_last_ctas = kPoolLastCtas;  // SPLASH_POOL_LANES, SPLASH_POOL_CTAS
+    int chain_fast = SPLASH_CHAIN_FAST;  // SPLASH_CHAIN_FAST=0/1: the pool's last stage on the branch-light day step (k_pool_spin)
     bool pool_auto = true;                // none of the four was set in the environment: preset by call size
     int two_pass = 1;                     // SPLASH_TWO_PASS
     int n_rounds = kRounds;               // SPLASH_ROUNDS_RT (<= kRounds)
@@ -1690,7 +1740,8 @@ cudaError_t prepare_kernels() {
     if ((e = cudaFuncSetAttribute(k_run_bulk<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem<FT>()))) return e;
     if ((e = cudaFuncSetAttribute(k_run_list<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
     if ((e = cudaFuncSetAttribute(k_run_list<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList))) return e;
-    if ((e = cudaFuncSetAttribute(k_pool_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_pool_spin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_pool_spin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))) return e;
     return cudaSuccess;
 }
 
@@ -1768,6 +1819,7 @@ static int ctx_create_impl(int device, splash_ctx* ctx, const cudaDeviceProp& pr
     if (const char* v = getenv("SPLASH_TWO_PASS")) ctx->two_pass = atoi(v) != 0;
     if (const char* v = getenv("SPLASH_POOL_STAGE2")) ctx->pool_stage2 = std::max(1, atoi(v));
     if (const char* v = getenv("SPLASH_POOL_LANES")) ctx->pool_last_lanes = std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("SPLASH_CHAIN_FAST")) ctx->chain_fast = atoi(v) != 0;
     if (const char* v = getenv("SPLASH_POOL_CTAS")) ctx->pool_last_ctas = std::max(1, atoi(v));
     {
         // a quarter of the SM's shared memory per last-stage CTA: four of them fill an SM, and none fits
@@ -1864,7 +1916,7 @@ int splash_debug_math(splash_ctx* ctx, int op, int64_t n, const double* x, doubl
         ctx->err = lane->err;
         return rc;
     }
-    if (!ctx || !x || !y || n < 0 || op < 0 || op > 3) return SPLASH_ERR_BAD_ARG;
+    if (!ctx || !x || !y || n < 0 || op < 0 || op > 10) return SPLASH_ERR_BAD_ARG;
     if (n == 0) return SPLASH_OK;
     CU(cudaSetDevice(ctx->device));
     TmpDev dx, dy;  // freed on every return path
@@ -2640,10 +2692,18 @@ struct GridJob {
             const int s1 = small_call ? kPoolStage1Small : ctx->pool_stage1, s2 = small_call ? kPoolStage2Small : ctx->pool_stage2;
             const int lanes3 = small_call ? kPoolLastLanesSmall : ctx->pool_last_lanes, ctas3 = small_call ? kPoolLastCtasSmall : ctx->pool_last_ctas;
             const int b1 = s1 > 0 ? s1 : (1 << 30);
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1, b1, 32);
+            k_pool_spin<false><<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 1, b1, 32, 0, 0);
             CU(cudaEventRecord(e.ps1, Q));
-            k_pool_spin<<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, s2, 32);
-            k_pool_spin<<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, lanes3);
+            k_pool_spin<false><<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, s2, 32, 0, 0);
+            if (ctx->chain_fast) {  // probe pass, then the fast route and the guarded route side by side (see k_pool_spin)
+                const int ctas_b = std::max(8, ctas3 / 4);
+                k_pool_spin<true><<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, kStageProbe, 1, lanes3, 0, 0);
+                k_pool_spin<true><<<(unsigned)(ctas3 + ctas_b), kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, kStageFinal, 1 << 30, lanes3, ctas3,
+                                                                                                    kPoolDeclinerLanes);
+                ++launches;
+            } else {
+                k_pool_spin<false><<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, lanes3, 0, 0);
+            }
             CU(cudaEventRecord(e.ps2, Q));
             CU(cudaGetLastError());
             launches += 4;
@@ -2879,9 +2939,9 @@ struct GridJob {
                     return cudaEventElapsedTime(&m, ev_begin, x) == cudaSuccess ? (double)m : -1.0;
                 };
                 fprintf(stderr,
-                        "[splash trace] tile %2lld: start %7.1f first %7.1f..%7.1f rounds_end %7.1f bulk %7.1f..%7.1f | pool n=%llu stage3=%llu "
+                        "[splash trace] tile %2lld: start %7.1f first %7.1f..%7.1f rounds_end %7.1f bulk %7.1f..%7.1f | pool n=%llu last_stage=%llu declining=%llu "
                         "stage1_end %7.1f stage2_end %7.1f main_end %7.1f max_chain %llu\n",
-                        (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n[2],
+                        (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n[2], c.decl_n,
                         opts.skip_spinup ? -1.0 : at(e.ps1), opts.skip_spinup ? -1.0 : at(e.ps2), opts.skip_spinup ? -1.0 : at(e.pm), c.max_chain);
             }
         }

@@ -46,6 +46,11 @@
 #ifndef SPLASH_L1_RECIP
 #define SPLASH_L1_RECIP (SPLASH_LEVEL >= 1)  // reciprocals of per-cell constants, consistent theta scaling
 #endif
+// SPLASH_FAST_STATE: the uniform kernels' state half through day_state_fast (branch-light, same bits) with day_state as
+// the fallback; the straggler chain has its own switch (SPLASH_CHAIN_FAST, splash_cuda.cu)
+#ifndef SPLASH_FAST_STATE
+#define SPLASH_FAST_STATE 0
+#endif
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -1013,6 +1018,362 @@ __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellSta
 #undef SPLASH_DIV_AI
 }
 
+// ------------------------------------------------------------------------------------------------
+// The branch-light state half (level 1 only).
+//
+// day_state above is ~100 basic blocks: every transcendental and every guarded division carries its own range check
+// and fallback branch, and every `if` of the reference is a branch.  A scheduler's warps then each run ONE dependent
+// FP64 chain (ncu r02: 3.6 cycles of fixed-latency wait per issued instruction at four warps per scheduler; for the
+// straggler chain, one warp per scheduler, every cycle of it is exposed).  day_state_fast computes the same values with
+// the same operations, organised so that independent chains share a basic block and overlap:
+//   * the fast-range bodies of exp/log/acos/fdiv (splash_math.cuh) without their guards; every guard is and-ed into
+//     one flag `ok`, gated by the condition under which the guarded value is actually used;
+//   * the reference's two-way and three-way `if`s as selects over both results;
+//   * the blocks that are rare and long stay branches and keep the guarded primitives: infiltration excess (inf_GA),
+//     the clamped-water-table tail of the transmittance, the second transmittance when the upslope input moved sm.
+// When `ok` comes out false (a NaN, a zero denominator, an argument outside a fast range: the reference's failsafe
+// territory) nothing has been written and the caller runs day_state on the same inputs.  Selected paths perform
+// day_state's operations in day_state's order, so both routes give the same bits (tools/emul_snapshot.py, the host
+// build with -DSPLASH_FAST_STATE=0/1; tests/test_level1_host_cpu.py).
+// ------------------------------------------------------------------------------------------------
+#if SPLASH_L1_POW && SPLASH_L1_RECIP
+#ifdef SPLASH_HOST_EMUL
+// host build only: how often each guard sends a day to the guarded path (tools/fast_state_stats.py)
+extern "C" long long g_fast_guard_trips[32];
+extern "C" long long g_fast_days;
+#define SPLASH_GUARD(k, cond)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            ok = false;                                        \
+            __atomic_fetch_add(&g_fast_guard_trips[k], 1LL, __ATOMIC_RELAXED); \
+        }                                                      \
+    } while (0)
+#else
+#define SPLASH_GUARD(k, cond) ok = ok & (cond)  // (conditions are written with | and &: no short-circuit branches)
+#endif
+
+template <class M, class CC>
+__device__ __forceinline__ Transm column_transmittance_fast(const CC& cc, double sm, double kbe3, bool& ok_io) {
+    bool ok = ok_io;
+    const double bub = cc(C_BUB);
+    const double e3 = cc(C_E3);
+    const double depth = cc(C_DEPTH);
+    Transm r;
+    const double theta_i = SPLASH_DIV_D1000(sm);
+    const double x = SPLASH_DIV_DTH(theta_i - cc(C_THR));
+    const double a = cc(C_ILAM) * fm::log_body(x);
+    const double e3a = e3 * a;
+    // Two regimes of a column at (or a rounding error below) its residual moisture are closed forms of the guarded
+    // route, which reaches them through its IEEE fallbacks every day the soil stays that dry:
+    //   negx  x < 0: log x, psi_m, wtd, both powers and dr are NaN -> wtd takes the `wtd < 0 || isnan` clamp (0.01)
+    //         and T_uns the `< 0 || isnan` failsafe (0)
+    //   dry   x == 0, or x^(1/lambda) underflows to 0 (a <= -746): psi_m = bub / 0 = -inf, wtd = +inf clamps to the
+    //         depth, the first power is exp(e3 a) = 0 and the second is built on (-inf) / (-inf) = NaN, so dr is
+    //         NaN and T_uns again the failsafe's 0.  Needs bub < 0, e3 > 0 and 1/lambda > 0, which holds for every
+    //         soil the pedotransfer functions return but is checked (a zero air-entry pressure goes the guarded way).
+    const bool negx = (x < 0.0);
+    const bool regular = (bub < 0.0) & (e3 > 0.0) & (cc(C_ILAM) > 0.0) & (cc(C_ILAM) < INFINITY) & (depth < INFINITY);
+    const bool dry = regular & ((x == 0.0) | (fm::log_ok(x) & (a <= -746.0) & (e3a <= -746.0)));
+    const bool closed = negx | dry;
+    SPLASH_GUARD(16, closed | fm::log_ok(x));
+    SPLASH_GUARD(17, closed | fm::exp_ok(a));
+    const double ea = fm::exp_body(a);
+    SPLASH_GUARD(18, closed | fm::fdiv_ok(ea));
+    const double psi_m = bub * fm::rcp(ea);
+    const double wtd0 = SPLASH_DIV_1000(bub - psi_m);
+    const bool below = (wtd0 < 0.0) | isnan(wtd0);
+    const bool above = !below & (wtd0 > depth);
+    const bool clamped = below | above;
+    const double wtd = negx ? kD.k_01b : (dry ? depth : (below ? kD.k_01b : (above ? depth : wtd0)));
+    r.acs_out = (depth - wtd) * cc(C_SIDOCT) * cc(C_CELLOUT);
+    SPLASH_GUARD(19, closed | fm::exp_ok(e3a));
+    const double r1 = fm::exp_body(e3a);
+    const double den = psi_m + (wtd * 1000.0);
+    // water table inside the column: the second base is 1 up to rounding noise, first-order expansion
+    const double qq = bub * fm::rcp(den);
+    const double qm1 = qq - 1.0;
+    double dr = r1 - (1.0 + e3 * qm1);
+    const bool expansion = fm::fdiv_ok(den) & (fabs(qm1) < kD.k_1em7);
+    if ((clamped | !expansion) & !closed) {  // the rare, long cases as in column_transmittance_core
+        if (clamped) {
+            const double t = e3 * M::log(SPLASH_FDIV(psi_m, den));
+            const double em1 = (fabs(t) < kD.k_1em5) ? t * (1.0 + 0.5 * t) : M::exp(t) - 1.0;
+            dr = -(r1 * em1);
+        } else {
+            const double q = SPLASH_FDIV(bub, den);
+            const double q1 = q - 1.0;
+            const double r2 = (fabs(q1) < kD.k_1em7) ? (1.0 + e3 * q1) : M::exp(e3 * M::log(q));
+            dr = r1 - r2;
+        }
+    }
+    double t_uns = kbe3 * dr;
+    t_uns *= cc(C_CT);
+    r.t_uns = (closed | (t_uns < 0.0) | isnan(t_uns)) ? 0.0 : t_uns;
+    ok_io = ok;
+    return r;
+}
+
+// returns false (st, o untouched) when the day needs the guarded path
+template <class M, class CC>
+__device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, CellState& st, DayOut& o) {
+    bool ok = true;
+    const double wn = st.wn;
+    const double tc = q.tc;
+    const double Ksat_visc = q.ksat_visc;
+    const double theta_s = cc(C_THS), theta_r = cc(C_THR);
+    const double theta_mean = SPLASH_DIV_D1000(wn);
+    const double theta_i =
+        (theta_mean >= theta_s) ? theta_s - kD.k_001 : ((theta_mean <= theta_r) ? theta_r + kD.k_001 : theta_mean);
+    // the two IEEE divisions of the day (fm::div_body: the compiler's own sequence without its fix-up branch)
+    const double theta_m = cxx_max(cc(C_THWMAX), theta_i);
+    const double ku_ratio = fm::div_body(theta_m, theta_s);
+    const double kb_num = Ksat_visc * cc(C_BUB);
+    // (a zero air-entry pressure: +-0 / e3 is a zero of the product's sign)
+    const bool kb_zero = (kb_num == 0.0) & fm::fdiv_ok(cc(C_E3));
+    SPLASH_GUARD(14, kb_zero | fm::div_ok(kb_num, cc(C_E3)));
+    const double kbe3 = kb_zero ? kb_num * ((cc(C_E3) > 0.0) ? 1.0 : -1.0) : fm::div_body(kb_num, cc(C_E3));
+    double sw = ((wn - cc(C_RES)) * cc(C_INV_WMR));
+    sw = ((sw < 0.0) | isnan(sw)) ? 0.0 : ((sw > 1.0) ? 1.0 : sw);
+    const double nd = (q.snowfall > 0.0) ? 0.0 : st.nd + 1.0;
+    double snow = st.snow + q.snowfall;
+
+    // ---- chain A: albedo -> shortwave -> net radiation cross-over hour angle ---------------------------------
+    const double ru = q.ru, rv = q.rv, hs = q.hs, sin_hs = q.sin_hs, rnl = q.rnl;
+    const int ndi = (int)nd;
+    SPLASH_GUARD(0, (nd >= 0.0) & ((double)ndi == nd));  // else: snow_age_factor's formula path
+    const double saf = (ndi < kSnowAgeTab) ? g_snow_age_tab[ndi & (kSnowAgeTab - 1)] : 0.0;  // exp(-0.895 nd) == 0 beyond
+    const double max_alb_snw = kD.alb_a + (kD.alb_b * saf);
+    const double d_sfc = 140.0 + snow;
+    SPLASH_GUARD(1, fm::fdiv_ok(d_sfc));
+    const double sfc = snow * fm::rcp(d_sfc);
+    const double alb_v = kD.alb_sw - kD.alb_c * sw;
+    const double alb = alb_v * (1.0 - sfc) + sfc * max_alb_snw;
+    const double rw = (q.rw_dark != 0.0) ? (1.0 - alb) * q.tau * q.dr * kD.gsc : (1.0 - alb) * (q.r_in) * q.inv_rw_den;
+    const double rwrv = rw * rv;
+    SPLASH_GUARD(2, fm::fdiv_ok(rwrv));
+    const double inv_rwrv = 1.0 * fm::rcp(rwrv);
+    const double qn = (rnl - rw * ru) * inv_rwrv;
+    const bool qn_hi = (qn >= 1.0), qn_lo = (qn <= -1.0);
+    SPLASH_GUARD(3, qn_hi | qn_lo | fm::acos_ok(qn));
+    // (every arm of a select is a value computed beforehand: `c ? a : f(x)` would be a branch around f)
+    const double hn_mid = SPLASH_TO_DEG(fm::acos_body(qn));
+    const double sq_hn = (1.0 - qn) * (1.0 + qn);
+    const double sin_hn_mid = fm::sqrt_body(sq_hn);
+    SPLASH_GUARD(15, qn_hi | qn_lo | fm::sqrt_ok(sq_hn));
+    const double hn = qn_hi ? 0.0 : (qn_lo ? 180.0 : hn_mid);
+    const double sin_hn = qn_hi ? 0.0 : (qn_lo ? SPLASH_SIN_180 : sin_hn_mid);
+    double rn_d = kD.pir * hn * (rw * ru - rnl) + rw * rv * sin_hn;
+    rn_d *= kD.k_ra;
+    double rnn_d = rw * rv * (sin_hs - sin_hn);
+    rnn_d += rw * ru * (hs - hn) * kD.pir;
+    rnn_d -= rnl * (kD.k_pi - hn * kD.pir);
+    rnn_d *= kD.k_ra;
+    const double s = q.s, g = q.g, econ = q.econ, pw = q.pw, rx = q.rx;
+    const double cn = (1.0e3) * econ * fabs(rnn_d) * kD.k_01;
+    const double eet_d = q.eet_k * rn_d;
+    const double pet_max = rx * ((rw * (ru + rv)) - rnl);
+    const double ef_den = g + sw * s;
+    SPLASH_GUARD(4, fm::fdiv_ok(ef_den));
+    const double EF = (sw * s) * fm::rcp(ef_den);
+    double swp = pet_max * EF;
+    swp = ((swp < 0.0) | isnan(swp)) ? 0.0 : swp;
+    const double cos_hi = swp * inv_rwrv * q.inv_rx + rnl * inv_rwrv - q.ruv;
+    const bool ch_hi = (cos_hi >= 1.0), ch_lo = (cos_hi <= -1.0);
+    SPLASH_GUARD(5, ch_hi | ch_lo | fm::acos_ok(cos_hi));
+    const double hi_mid = SPLASH_TO_DEG(fm::acos_body(cos_hi));
+    const double sq_hi = (1.0 - cos_hi) * (1.0 + cos_hi);
+    const double sin_hi_mid = fm::sqrt_body(sq_hi);
+    SPLASH_GUARD(21, ch_hi | ch_lo | fm::sqrt_ok(sq_hi));
+    const double hi = ch_hi ? 0.0 : (ch_lo ? 180.0 : hi_mid);
+    const double sin_hi = ch_hi ? 0.0 : (ch_lo ? SPLASH_SIN_180 : sin_hi_mid);
+    const double melt_cap = cxx_min(snow, (rn_d * q.inv_pwk) * 1000.0);
+    const double snowmelt_tot = (tc >= 3.0) ? melt_cap : 0.0;
+    double melt_enrg = SPLASH_DIVC_1000(snowmelt_tot) * pw * kkfus;
+    const double AE = rn_d - melt_enrg;
+    const double sublimation = cxx_min(snowmelt_tot, (AE * econ) * 1000.0);
+    melt_enrg += SPLASH_DIVC_1000(sublimation) * q.inv_econ;
+    double aet_d = swp * hi * kD.pir;
+    aet_d += rx * rw * rv * (sin_hn - sin_hi);
+    aet_d += (rx * rw * ru - rx * rnl) * (hn - hi) * kD.pir;
+    aet_d *= kD.k_24pi;
+    const double aet_fix = 0.0 - sublimation, aet_gen = aet_d - (melt_enrg * econ * 1000.0);
+    aet_d = ((aet_d == 0.0) & (snowmelt_tot == 0.0)) ? aet_fix : aet_gen;
+    aet_d = (aet_d < 0.0) ? 0.0 : aet_d;
+    snow -= snowmelt_tot;
+    const double snowmelt = snowmelt_tot - sublimation;
+    const double inflow = q.rain + cn + snowmelt;
+
+    // ---- chain B: moist_surf (two logs, two exps of the relative saturation) ---------------------------------
+    double surf_moist;
+    {
+        const double xms = SPLASH_DIV_DTH(theta_mean - theta_r);
+        const bool below = (theta_mean < theta_r);  // the result is theta_r whatever the powers give
+        const double lx = fm::log_body(xms);
+        const double a1 = -(cc(C_ILAM) * lx);
+        const double inv_u = fm::exp_body(a1);
+        double head = inv_u + cc(C_TEN_BP);
+        head = (inv_u > fabs(cc(C_TEN_BP)) * kD.k_ovf) ? INFINITY : head;
+        const double a2 = cc(C_NLAM) * fm::log_body(head);
+        const double hp = fm::exp_body(a2);
+        // a negative head (|10 / bp| > 1/u: a coarse soil near saturation) makes log, the power and theta_BC NaN, which the
+        // reference's failsafe turns into theta_s
+        const bool neg_head = (head < 0.0) & (head > -INFINITY);
+        // at the residual moisture (x == 0) or with 1/u = exp(a1) overflowing (a1 >= 710) the head is +inf and
+        // (head/bp)^(-lambda) = exp(-lambda * inf) = 0: theta_BC = DTH * 0 + theta_r (for lambda > 0, 1/lambda > 0)
+        const bool inf_head = ((xms == 0.0) | (fm::log_ok(xms) & (a1 >= 710.0))) & (cc(C_ILAM) > 0.0) & (cc(C_NLAM) < 0.0) &
+                              (cc(C_NLAM) > -INFINITY) & (fabs(cc(C_DTH)) < INFINITY);
+        SPLASH_GUARD(6, below | inf_head | (fm::log_ok(xms) & fm::exp_ok(a1)));
+        SPLASH_GUARD(7, below | inf_head | neg_head | fm::log_ok(head));  // (head == 0, +-inf: guarded path)
+        SPLASH_GUARD(12, below | inf_head | !fm::log_ok(head) | fm::exp_ok(a2));
+        const double theta_BC = cc(C_DTH) * (inf_head ? 0.0 : hp) + theta_r;
+        surf_moist = below ? theta_r : ((!inf_head & (neg_head | isnan(theta_BC))) ? theta_s : theta_BC);
+    }
+
+    // ---- chain C: Kunsat above field capacity (deep columns) -------------------------------------------------
+    const bool deep = (cc(C_DEPTH) >= 2.0);
+    const bool ku_const = (theta_i <= cc(C_THWMAX)) | isnan(theta_i);
+    const double ku_l = cc(C_KUEXP) * fm::log_body(ku_ratio);
+    SPLASH_GUARD(8, !deep | ku_const | (fm::div_ok(theta_m, theta_s) & fm::log_ok(ku_ratio) & fm::exp_ok(ku_l)));
+    const double kp_pow = fm::exp_body(ku_l);
+    const double kp = ku_const ? cc(C_KU_WMAX) : kp_pow;
+    const double Kunsat = deep ? Ksat_visc * kp : 0.0;
+
+    // ---- chain D: recession constant (forcing and constants only) --------------------------------------------
+    const double hyd_grad_in = cc(C_TAN_S);
+    const double T_q0 = kbe3 * cc(C_BRQ0);
+    const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
+    const double Q_qs = SPLASH_DIVC_1000(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS));
+    const double z_kb = (Q_q0 - Q_qs) * cc(C_INV_DENKB);
+    const bool kb_small = (fabs(z_kb) < 0x1p-20);
+    SPLASH_GUARD(9, kb_small | fm::exp_ok(z_kb) | isnan(z_kb));  // (exp_body(NaN) is NaN like exp(NaN))
+    const double kb_series = 1.0 + fma(0.5 * z_kb, z_kb, z_kb), kb_exp = fm::exp_body(z_kb);
+    const double Kb = kb_small ? kb_series : kb_exp;
+    const double lkb = fm::log_body(Kb);  // used (and its guard counted) on drainage days only
+    const double To_uns = kbe3 * cc(C_BRW);
+    const double Qo_uns = To_uns * cc(C_CW);
+    const double Qo_sat = SPLASH_DIVC_1000(Ksat_visc * 24.0 * cc(C_ACSW));
+
+    // ---- inf_GA, SPLASH.cpp:1984-2022: the infiltration-excess case stays a branch ---------------------------
+    double infi;
+    {
+        const double P = inflow;
+        const double r = SPLASH_DIVC_6(P);
+        const double h_f = cc(C_HF);
+        const double delta_theta = (theta_s - surf_moist);
+        double I = (r <= Ksat_visc) ? P : Ksat_visc * 6.0;
+        if (!(r <= Ksat_visc) && !(delta_theta <= 0.0)) {
+            double tp = SPLASH_FDIV(Ksat_visc * delta_theta * -1.0 * h_f, r * (r - Ksat_visc));
+            if (tp <= 0.0 || isnan(tp)) {
+                tp = kD.k_01b;
+            }
+            const double tp_s = tp / cc(C_COS2_S);
+            I = r * tp_s + (Ksat_visc * (6.0 - tp_s) - (h_f * delta_theta * M::log(1 - SPLASH_FDIV(r * tp_s, h_f * delta_theta))));
+        }
+        infi = (I > P) ? P : I;
+    }
+    const double ro_h = cxx_max(inflow - infi, 0.0);
+    double R = infi - aet_d;
+    const double hyd_grad_z = infi * q.inv_k24 - 1.0;
+    const double hg2 = (hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in);
+    SPLASH_GUARD(22, fm::sqrt_ok(hg2));
+    const double hyd_grad_out = fm::sqrt_body(hg2);
+    const double Qt = (Qo_sat + Qo_uns) * hyd_grad_out;
+    const double qin_kb = st.qin * Kb;
+    const double q_in_o = ((st.td <= 0.0) | (st.qin <= 0.0)) ? 0.0 : qin_kb;
+    const double SAT = cc(C_SAT), RES = cc(C_RES);
+    double sm = wn + q_in_o + R;
+    const bool over = (sm > SAT);
+    const double excess = sm - SAT;
+    double ro_d = over ? excess : 0.0;
+    const double R_less = R - ro_d;
+    R = (over & (R > 0)) ? R_less : R;
+    sm = over ? SAT : ((sm < RES) ? RES : sm);
+    const double Ai = cc(C_AI);
+    Transm tr = column_transmittance_fast<M>(cc, sm, kbe3, ok);
+    double T;
+    {
+        const double T_uns = deep ? tr.t_uns + Kunsat * 24.0 : tr.t_uns;
+        const double T_sat = Ksat_visc * 24.0 * ((deep ? tr.acs_out + Ai : tr.acs_out) * cc(C_INV_AI));
+        T = (T_sat + T_uns) * hyd_grad_out;
+    }
+    const double Q = SPLASH_DIVC_1000(T * Ai);
+    // ---- 5.7 same-day upslope input, :1465-1483 --------------------------------------------------------------
+    const double td = st.td - 1.0;
+    const bool drain = (R > 0.0) & (sm > cc(C_WMAX));
+    const double AuR = cc(C_AU) * R;
+    const double arg = 1.0 - (lkb * (AuR * fm::rcp(Q)));
+    // flat cells: Kb == 1, log Kb == 0 and t_drain = -log(1 - 0 * x) / 0 is NaN whatever x is (0/0, or NaN/0)
+    const bool lkb_zero = (lkb == 0.0);
+    // no outflow at all (Q == +0: a column whose transmittance is the failsafe's 0): Au R / 0 = +inf; for lkb < 0 the
+    // argument of the logarithm is 1 - lkb * inf = +inf and t_drain = (-inf) / lkb = +inf, for lkb > 0 it is -inf and
+    // the logarithm, hence t_drain, NaN
+    const bool q_zero = (__double_as_longlong(Q) == 0LL) & (AuR > 0.0) & (AuR < INFINITY) & fm::fdiv_ok(lkb);
+    // a negative argument gives log = NaN and t_drain = NaN (lkb finite)
+    const bool arg_neg = (arg < 0.0) & fm::fdiv_ok(Q) & fm::fdiv_ok(lkb);
+    SPLASH_GUARD(10, !drain | (fm::log_ok(Kb) & (lkb_zero | q_zero | fm::fdiv_ok(Q))));
+    SPLASH_GUARD(11, !drain | lkb_zero | q_zero | arg_neg | (fm::log_ok(arg) & fm::fdiv_ok(lkb)));
+    const double t_drain_v = (-1.0 * fm::log_body(arg)) * fm::rcp(lkb);
+    const double t_drain = drain ? ((lkb_zero | arg_neg | (q_zero & (lkb > 0.0))) ? nan("") : (q_zero ? INFINITY : t_drain_v)) : 0.0;
+    const double q_in_f_v = (Qt - AuR * lkb) * cc(C_INV_AI);
+    double q_in_f = drain ? q_in_f_v : 0.0;
+    q_in_f = ((q_in_f < 0.0) | isnan(q_in_f)) ? 0.0 : q_in_f;
+    const double tdrain_out = cxx_max((td + t_drain) / 2, 0.0);
+    // ---- 5.8 update soil moisture, :1488-1506 ----------------------------------------------------------------
+    const double sm_before = sm;
+    sm += (q_in_f);
+    const bool over2 = (sm > SAT);
+    const double ro_d2 = ro_d + (sm - SAT);
+    ro_d = over2 ? ro_d2 : ro_d;
+    sm = over2 ? SAT : ((sm < RES) ? RES : sm);
+    const double ro = ro_d + ro_h;
+    if (!(sm == sm_before)) {
+        tr = column_transmittance_fast<M>(cc, sm, kbe3, ok);
+    }
+    {
+        const double T_sat = Ksat_visc * 24.0 * (tr.acs_out * cc(C_INV_AI));
+        T = (T_sat + tr.t_uns) * hyd_grad_out;
+    }
+    sm -= (T);
+    sm = (sm > SAT) ? SAT : ((sm < RES) ? RES : sm);
+#ifdef SPLASH_HOST_EMUL
+    __atomic_fetch_add(&g_fast_days, 1LL, __ATOMIC_RELAXED);
+#endif
+    if (!ok) return false;
+    st.wn = sm;
+    st.snow = snow;
+    st.qin = cxx_max(cxx_max(q_in_o, q_in_f), 0.0);
+    st.td = tdrain_out;
+    st.nd = nd;
+    o.ro = ro;
+    o.pet = eet_d;
+    o.aet = aet_d;
+    o.cond = cn;
+    o.bflow = T;
+    o.netr = SPLASH_DIVC_1E6(rn_d);
+    return true;
+}
+#undef SPLASH_GUARD
+
+// the state half as the kernels call it: the branch-light route when `try_fast`, and the guarded route (one inline
+// copy behind it: no call, the day's inputs stay in their registers) for the days it declines.  Returns whether the
+// branch-light route took the day.
+template <class M, class CC>
+__device__ __forceinline__ bool day_state_auto(const CC& cc, const DayPre& q, CellState& st, DayOut& o, bool try_fast = true) {
+    bool done = false;
+    if (try_fast) done = day_state_fast<M>(cc, q, st, o);
+#ifndef SPLASH_FAST_NOFALLBACK  // (defined for timing experiments only: wrong results on the days the fast route declines)
+    if (!done) day_state<M>(cc, q, st, o);
+#endif
+    return done;
+}
+#else
+template <class M, class CC>
+__device__ __forceinline__ bool day_state_auto(const CC& cc, const DayPre& q, CellState& st, DayOut& o, bool try_fast = true) {
+    day_state<M>(cc, q, st, o);
+    return false;
+}
+#endif
+
 //   st     state in/out;  o  fluxes of the day;  rain_out / snowfall_out  the partitioned precipitation
 //   (for the aridity index and the occurrence flags)
 // The uniform kernels expand the transcendentals in place, as the chain kernel does (measured +6 % over the shared
@@ -1032,7 +1393,11 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     day_forcing<DayMath>(cc, dt, mt, sw_in, tc, pn, q);
     rain_out = q.rain;
     snowfall_out = q.snowfall;
+#if SPLASH_FAST_STATE
+    day_state_auto<DayMath>(cc, q, st, o);
+#else
     day_state<DayMath>(cc, q, st, o);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,6 +11,12 @@
 #include <vector>
 
 #include "../../include/splash_cuda.h"
+namespace splash {
+extern "C" {
+long long g_fast_guard_trips[32];  // day_state_fast: days sent to the guarded path, per guard
+long long g_fast_days;
+}
+}  // namespace splash
 #include "../../rsplash_b200/csrc/splash_model.cuh"
 #include "../../rsplash_b200/csrc/splash_host_tables.h"
 
@@ -36,6 +42,12 @@ double ld(const void* base, int64_t i) { return (double)((const FT*)base)[i]; }
 }  // namespace
 
 extern "C" int splash_emul_level(void) { return SPLASH_LEVEL; }
+extern "C" int splash_emul_fast_state(void) { return SPLASH_FAST_STATE; }
+extern "C" void splash_emul_fast_stats(long long* days, long long* trips) {  // and reset
+    *days = g_fast_days;
+    g_fast_days = 0;
+    for (int k = 0; k < 32; ++k) { trips[k] = g_fast_guard_trips[k]; g_fast_guard_trips[k] = 0; }
+}
 
 // SPLASH_EMUL_TRACE=<file>: one line per day step in the order SPLASH::spin_up / run_all call run_one_day (the
 // first spin_up's own equilibrium loop included, and each check day repeated as day 1 of the pass it starts), so

@@ -13,8 +13,8 @@ CSRC = os.path.join(ROOT, "rsplash_b200", "csrc")
 _libs = {}
 
 
-def build(level: int = 1) -> str:
-    out = os.path.join(ROOT, "tests", "_build", f"libsplash_emul_l{level}.so")
+def build(level: int = 1, fast: int = 0) -> str:
+    out = os.path.join(ROOT, "tests", "_build", f"libsplash_emul_l{level}{'f' if fast else ''}.so")
     deps = [os.path.join(SRC_DIR, f) for f in ("emul.cpp", "cuda_runtime.h")] + \
            [os.path.join(CSRC, f) for f in ("splash_model.cuh", "splash_math.cuh", "splash_consts.cuh", "splash_host_tables.h")] + \
            [os.path.join(ROOT, "include", "splash_cuda.h")]
@@ -22,7 +22,7 @@ def build(level: int = 1) -> str:
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-mfma", "-fopenmp", "-fPIC", "-shared", "-DSPLASH_HOST_EMUL",
-           f"-DSPLASH_LEVEL={level}", "-I" + SRC_DIR, "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-o", out,
+           f"-DSPLASH_LEVEL={level}", f"-DSPLASH_FAST_STATE={fast}", "-I" + SRC_DIR, "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-o", out,
            os.path.join(SRC_DIR, "emul.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -30,17 +30,27 @@ def build(level: int = 1) -> str:
     return out
 
 
-def lib(level: int = 1):
-    if level not in _libs:
-        L = C.CDLL(build(level))
+def lib(level: int = 1, fast: int = 0):
+    key = (level, fast)
+    if key not in _libs:
+        L = C.CDLL(build(level, fast))
         L.splash_emul_grid_run.argtypes = [C.POINTER(_abi.SplashGridIn), C.POINTER(_abi.SplashOpts), C.POINTER(_abi.SplashGridOut)]
         L.splash_emul_grid_run.restype = C.c_int
-        assert L.splash_emul_level() == level
-        _libs[level] = L
-    return _libs[level]
+        assert L.splash_emul_level() == level and L.splash_emul_fast_state() == fast
+        _libs[key] = L
+    return _libs[key]
 
 
-def run(problem: ol.GridProblem, level: int = 1, state_init=None) -> dict:
+def fast_stats(level: int = 1):
+    """(days, trips[32]) of day_state_fast since the last call: how many day steps ran, and how many each guard sent
+    to the guarded path (host build with fast=1)."""
+    days = C.c_longlong()
+    trips = (C.c_longlong * 32)()
+    lib(level, 1).splash_emul_fast_stats(C.byref(days), trips)
+    return days.value, list(trips)
+
+
+def run(problem: ol.GridProblem, level: int = 1, state_init=None, fast: int = 0) -> dict:
     """The block through the host build of the device day step: daily outputs, state_final, cell_diag."""
     import numpy as np
 
@@ -50,7 +60,7 @@ def run(problem: ol.GridProblem, level: int = 1, state_init=None) -> dict:
         st = np.ascontiguousarray(state_init, dtype=np.float64)
         opts.skip_spinup, opts.state_init = 1, st.ctypes.data
     cin = problem.c_in()
-    rc = lib(level).splash_emul_grid_run(C.byref(cin), C.byref(opts), C.byref(cout))
+    rc = lib(level, fast).splash_emul_grid_run(C.byref(cin), C.byref(opts), C.byref(cout))
     if rc != 0:
         raise RuntimeError(f"host build of the day step failed rc={rc}")
     return arrays

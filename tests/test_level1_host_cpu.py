@@ -127,3 +127,20 @@ def test_zero_air_entry_pressure_host_build():
         assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])), k
     stable, _ = conditioning.stable_cells(prob, ref, conditioning.VARIANTS)
     _gates(got, ref, np.flatnonzero(stable))
+
+
+def test_branch_light_state_half_gives_the_bits_of_the_guarded_one():
+    """day_state_fast (the route of the straggler chain's last stage) against day_state on the host build: every output
+    of every cell bit for bit -- global, polar and tropical draws plus the real-data series -- and the share of days
+    it hands back to the guarded route stays small (the closed forms of the dry regimes are what keep it there)."""
+    probs = {"bourne": load_problem("bourne")[0], "syn": make_problem(900, 2, seed=77)[0],
+             "polar": make_problem(400, 1, seed=78, lat_range=(66.0, 89.0))[0],
+             "tropic": make_problem(400, 1, seed=79, lat_range=(-20.0, 20.0))[0]}
+    for name, prob in probs.items():
+        a = he.run(prob, level=1, fast=0)
+        he.fast_stats()
+        b = he.run(prob, level=1, fast=1)
+        days, trips = he.fast_stats()
+        for k in _abi.OUTPUT_NAMES + ("state_final", "cell_diag"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), (name, k)
+        assert days > 0 and sum(trips) <= 0.01 * days, (name, days, trips)

@@ -47,3 +47,27 @@ def test_special_values_follow_libdevice(ctx):
     r = ctx.debug_math("sin", [0.0, np.pi, np.nan, -0.3, 7.0])
     assert r[0] == 0.0 and abs(r[1] - 1.2246467991473532e-16) < 1e-30 and np.isnan(r[2])
     assert abs(r[3] - np.sin(-0.3)) < 1e-15 and abs(r[4] - np.sin(7.0)) < 1e-15
+
+
+def test_branch_free_bodies_equal_what_they_replace(ctx):
+    """day_state_fast (csrc/splash_model.cuh) calls the guard-free bodies: inside their guards they must give the bits
+    of the guarded functions, and sqrt / division the bits of the compiler's IEEE expansions."""
+    rng = np.random.default_rng(5)
+    n = 1 << 21
+    same = lambda a, b: np.array_equal(a, b, equal_nan=True)
+    x = np.concatenate([rng.uniform(-1.0, 1.0, n), np.nextafter(1.0, 0.0) * np.sign(rng.uniform(-1, 1, 64)), rng.uniform(-0.5, 0.5, n // 4) ** 3])
+    assert same(ctx.debug_math("acos_body", x), ctx.debug_math("acos", x))
+    x = np.concatenate([np.exp(rng.uniform(-600.0, 600.0, n)), rng.uniform(0.0, 4.0, n), 1.0 - rng.uniform(0.0, 1.0, n // 4) ** 8])
+    a, b = ctx.debug_math("sqrt_body", x), ctx.debug_math("sqrt", x)
+    assert same(a, b) and np.array_equal(b, np.sqrt(x))
+    x = np.concatenate([np.exp(rng.uniform(-300.0, 300.0, n)) * np.sign(rng.uniform(-1, 1, n)), rng.uniform(0.0, 1.0, n),
+                        rng.integers(1, 1 << 20, n).astype(np.float64)])
+    a, b = ctx.debug_math("div_body", x), ctx.debug_math("div", x)
+    assert same(a, b) and not np.isnan(a).all()
+    w = x[(np.arange(x.size, dtype=np.int64) * 7919 + 13) % x.size]
+    ok = ~np.isnan(b)
+    assert np.array_equal(b[ok], (x / w)[ok])
+    x = rng.uniform(-699.0, 699.0, n)
+    assert same(ctx.debug_math("exp_body", x), ctx.debug_math("exp", x))
+    x = np.exp(rng.uniform(-700.0, 700.0, n))
+    assert same(ctx.debug_math("log_body", x), ctx.debug_math("log", x))
