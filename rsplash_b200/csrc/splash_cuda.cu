@@ -89,8 +89,16 @@ constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
 // 112 / 120 / 128: faster bulk kernel alone (up to +15 %) but 3.1 - 3.9 s per pass, because pool warps and such CTAs then
 // exclude each other from an SM and the straggler chain ends after the bulk launches.  SPLASH_UREGS=0: launch bound.
 #ifndef SPLASH_UREGS
-#define SPLASH_UREGS 104
+#define SPLASH_UREGS (SPLASH_UTHREADS > 512 ? 80 : 104)
 #endif
+// the bulk launch (k_run_bulk) has its own shape, see kBThreads below
+#ifndef SPLASH_BULK_THREADS
+#define SPLASH_BULK_THREADS 768
+#endif
+#ifndef SPLASH_BULK_REGS
+#define SPLASH_BULK_REGS (SPLASH_BULK_THREADS > 512 ? 80 : 104)
+#endif
+#define SPLASH_BULK_BOUNDS __maxnreg__(SPLASH_BULK_REGS)
 #if SPLASH_UREGS > 0
 #define SPLASH_UNIFORM_BOUNDS __maxnreg__(SPLASH_UREGS)
 #else
@@ -125,6 +133,40 @@ struct StridedCC {  // column of a [NCC][stride] matrix (shared or global memory
     double* base;
     int64_t stride;
     __device__ __forceinline__ double& operator()(int k) const { return base[(int64_t)k * stride]; }
+};
+
+// Shapes of the uniform kernels.  The day step keeps 52 constants per cell; as private shared-memory columns they cap a
+// CTA at 512 cells (213 KB), i.e. four warps per scheduler -- too few to hide the FP64 dependency latency (ncu r02:
+// 3.6 cycles of fixed-latency wait per issued instruction).  A kernel compiled for more than 512 threads keeps only the
+// constants of the state half (the dependent chain) in shared memory and reads the 18 that the forcing half and the
+// output stage use -- state-independent, so their loads are issued at the top of the day and are not waited for until
+// the forcing half needs them -- from the constant matrix in global memory (L2 hits: 15 MB for the whole device).
+// The bulk launch runs 768 threads x 80 registers = six warps per scheduler (+8 % on the kernel alone, measured; the
+// spin-up kernels keep 512 threads: their late rounds are short lists, where larger CTAs were measured slower).
+constexpr int kBThreads = SPLASH_BULK_THREADS;
+template <int NT> __host__ __device__ constexpr bool hybrid_cc() { return NT > 512; }
+
+// constants that only day_forcing (and the output stage) read
+__host__ __device__ constexpr bool cc_cold(int k) {
+    return k == C_ELEV_K || k == C_LAT_K || k == C_TT || k == C_COS_LAT || k == C_SIN_LAT || k == C_SIN_S || k == C_COS_S ||
+           k == C_COS_A || k == C_SIN_A || k == C_TAU_O || k == C_TAU_A || k == C_PATM || k == C_PBAR || k == C_PBARF ||
+           k == C_VISC0 || k == C_INTPERM || k == C_INV_TAU_B || k == C_WRR;
+}
+__host__ __device__ constexpr int cc_hot_slot(int k) {  // rank of constant k among the hot ones
+    int n = 0;
+    for (int j = 0; j < k; ++j) n += cc_cold(j) ? 0 : 1;
+    return n;
+}
+constexpr int kHotCC = cc_hot_slot(NCC_DAY);
+
+template <int NT>
+struct HybridCC {  // read-only: hot constants from the thread's shared-memory column, cold ones from the global matrix
+    const double* hot;
+    const double* cold;  // p.cc + c
+    int64_t gstride;
+    __device__ __forceinline__ double operator()(int k) const {
+        return cc_cold(k) ? __ldg(cold + (int64_t)k * gstride) : hot[cc_hot_slot(k) * NT];
+    }
 };
 
 template <typename T>
@@ -414,13 +456,13 @@ struct BulkForcing {  // generic: raw values in registers (f64 forcing)
 
 template <>
 struct BulkForcing<float> {  // f32: cp.async ring in shared memory
-    float* ring = nullptr;   // [2][3][kUThreads], this thread's column
+    float* ring = nullptr;   // [2][3][kBThreads], this thread's column
     __device__ __forceinline__ void issue(const RunParams& p, int c, int d) {
-        float* slot = ring + (d & 1) * 3 * kUThreads;
+        float* slot = ring + (d & 1) * 3 * kBThreads;
         const int64_t off = (int64_t)d * p.fpitch + c;
         cp_async_f32(slot, (const float*)p.sw + off);
-        cp_async_f32(slot + kUThreads, (const float*)p.tc + (int64_t)d * p.tpitch + c);
-        cp_async_f32(slot + 2 * kUThreads, (const float*)p.pn + off);
+        cp_async_f32(slot + kBThreads, (const float*)p.tc + (int64_t)d * p.tpitch + c);
+        cp_async_f32(slot + 2 * kBThreads, (const float*)p.pn + off);
         cp_async_commit();
     }
     __device__ __forceinline__ void start(const RunParams& p, int c, bool live, void* smem_after_cc) {
@@ -431,10 +473,10 @@ struct BulkForcing<float> {  // f32: cp.async ring in shared memory
         f_sw = f_tc = f_pn = 0.0;
         if (!live) return;
         cp_async_wait_all();
-        const float* slot = ring + (d & 1) * 3 * kUThreads;
+        const float* slot = ring + (d & 1) * 3 * kBThreads;
         f_sw = (double)slot[0];
-        f_tc = (double)slot[kUThreads];
-        f_pn = (double)slot[2 * kUThreads];
+        f_tc = (double)slot[kBThreads];
+        f_pn = (double)slot[2 * kBThreads];
         if (d + 1 < p.n_days) issue(p, c, d + 1);
     }
 };
@@ -477,14 +519,54 @@ __device__ __forceinline__ bool spin_decide(const CellState& Ek, double chk_wn, 
     return cont;
 }
 
+// a uniform kernel's constants: all of them (StridedCC) or the hot ones (HybridCC) into the thread's shared-memory column
+template <int NT>
+__device__ __forceinline__ void stage_cc(const RunParams& p, int c, bool live, double* s_cc, StridedCC& cc) {
+    cc = StridedCC{s_cc + threadIdx.x, NT};
+    if (live) load_cc(p, c, cc);
+}
+template <int NT>
+__device__ __forceinline__ void stage_cc(const RunParams& p, int c, bool live, double* s_cc, HybridCC<NT>& cc) {
+    cc = HybridCC<NT>{s_cc + threadIdx.x, p.cc + c, p.cpitch};
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < NCC_DAY; ++k)
+            if (!cc_cold(k)) s_cc[cc_hot_slot(k) * NT + threadIdx.x] = p.cc[(int64_t)k * p.cpitch + c];
+    }
+}
+template <int NT> using ShapeCC = std::conditional_t<hybrid_cc<NT>(), HybridCC<NT>, StridedCC>;
+template <int NT> __host__ __device__ constexpr int staged_cc() { return hybrid_cc<NT>() ? kHotCC : (int)NCC_DAY; }  // constants per cell in shared memory
+
+// lateral_consts on a uniform kernel's constants: the four results go to the thread's shared-memory column and to the
+// constant matrix (HybridCC is read-only, so the arithmetic runs on a scratch copy of the three inputs)
+struct ScratchCC {
+    double v[NCC];
+    __device__ __forceinline__ double& operator()(int k) { return v[k]; }
+};
+template <int NT>
+__device__ __forceinline__ void apply_lateral(const RunParams& p, int c, double* s_cc, const ShapeCC<NT>& cc, double AI) {
+    ScratchCC t;
+    t(C_SIDOCT) = cc(C_SIDOCT);
+    t(C_DEPTH) = cc(C_DEPTH);
+    t(C_AI) = cc(C_AI);
+    lateral_consts(t, AI);
+    constexpr int out[4] = {C_CELLOUT, C_CQ0, C_ACSQS, C_CT};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = out[j];
+        s_cc[(hybrid_cc<NT>() ? cc_hot_slot(k) : k) * NT + threadIdx.x] = t(k);
+        p.cc[(int64_t)k * p.cpitch + c] = t(k);
+    }
+}
+
 // ---- K2a: aridity pass + pass 0 of the second spin_up, all cells, 730 uniform days ---------------
 template <typename FT>
 __global__ void SPLASH_UNIFORM_BOUNDS k_spin_first(RunParams p) {
     extern __shared__ double s_cc[];
     const int c = blockIdx.x * kUThreads + threadIdx.x;
     const bool live = c < p.n_cells;  // threads past the tile's end idle through the loop: every thread reaches every barrier
-    StridedCC cc{s_cc + threadIdx.x, kUThreads};
-    if (live) load_cc(p, c, cc);
+    ShapeCC<kUThreads> cc;
+    stage_cc<kUThreads>(p, live ? c : 0, live, s_cc, cc);
     const double RES = live ? cc(C_RES) : 0.0;
     CellState st;
     st.wn = RES;  // cold start of SPLASH::spin_up, SPLASH.cpp:1633-1639
@@ -512,11 +594,7 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_spin_first(RunParams p) {
             if (!isnan(P)) sum_p.add(P);
             if (it == kSpinYear - 1) {
                 AI = sum_pet.value() / sum_p.value();
-                lateral_consts(cc, AI);  // soil_info[12] <- AI lands in the `cellout` slot (SURVEY B-3)
-                p.cc[(int64_t)C_CELLOUT * p.cpitch + c] = cc(C_CELLOUT);
-                p.cc[(int64_t)C_CQ0 * p.cpitch + c] = cc(C_CQ0);
-                p.cc[(int64_t)C_ACSQS * p.cpitch + c] = cc(C_ACSQS);
-                p.cc[(int64_t)C_CT * p.cpitch + c] = cc(C_CT);
+                apply_lateral<kUThreads>(p, c, s_cc, cc, AI);  // soil_info[12] <- AI lands in the `cellout` slot (SURVEY B-3)
                 st.wn = RES;
                 st.snow = st.qin = st.td = st.nd = 0.0;
             }
@@ -586,12 +664,10 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_spin_rest(RunParams p) {
     const bool live = i < n_list;  // the list's last CTA: idle threads still reach every barrier
     const int c = live ? p.lists[(r + 1) & 1][i] : 0;
     SPLASH_CHECK(c >= 0 && c < p.n_cells && n_list <= (unsigned long long)p.n_cells, 103);
-    StridedCC cc{s_cc + threadIdx.x, kUThreads};
+    ShapeCC<kUThreads> cc;
+    stage_cc<kUThreads>(p, c, live, s_cc, cc);
     CellState st{};
-    if (live) {
-        load_cc(p, c, cc);
-        st = load_state(p.w, c);
-    }
+    if (live) st = load_state(p.w, c);
     RawForcing<FT> nxt{};
     if (live) nxt = ld_raw_spin<FT>(p, c, 1);
     for (int d = 1; d < kSpinYear; ++d) {
@@ -665,10 +741,9 @@ __device__ __forceinline__ void emit_day(const RunParams& p, int c, int d, const
 // frost and snow frequency, aridity); without an order (the default: the sort was measured slower on the synthetic grid,
 // whose divergence is day-to-day weather, not regime), cell i.
 template <typename FT, bool kMonthly>
-__global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
+__global__ void SPLASH_BULK_BOUNDS k_run_bulk(RunParams p) {
     extern __shared__ double s_cc[];
-    StridedCC cc{s_cc + threadIdx.x, kUThreads};
-    const long long i0 = (long long)blockIdx.x * kUThreads;
+    const long long i0 = (long long)blockIdx.x * kBThreads;
     const long long n_run = p.order ? (long long)p.ctl->n_ready : (long long)p.n_cells;
     if (i0 >= n_run) return;  // surplus CTA: all of its threads leave together
     const long long i = i0 + threadIdx.x;
@@ -679,10 +754,11 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
         SPLASH_CHECK(c >= 0 && c < p.n_cells && n_run <= (long long)p.n_cells, 104);
         live = p.w.status[c] == ST_READY_BULK;
     }
+    ShapeCC<kBThreads> cc;
+    stage_cc<kBThreads>(p, c, live, s_cc, cc);
     CellState st{};
     double RES = 0.0, wrr = 1.0;
     if (live) {
-        load_cc(p, c, cc);
         RES = cc(C_RES);
         wrr = cc(C_WRR);
         st = load_state(p.w, c);
@@ -691,7 +767,7 @@ __global__ void SPLASH_UNIFORM_BOUNDS k_run_bulk(RunParams p) {
     MonthAcc macc;
     macc.clear();
     BulkForcing<FT> pipe;
-    pipe.start(p, c, live, s_cc + (size_t)NCC_DAY * kUThreads);
+    pipe.start(p, c, live, s_cc + (size_t)staged_cc<kBThreads>() * kBThreads);
     for (int d = 0; d < p.n_days; ++d) {
         double f_sw, f_tc, f_pn;
         pipe.next(p, c, d, live, f_sw, f_tc, f_pn);
@@ -971,7 +1047,7 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
     }
 }
 
-constexpr int kFastDeclineLimit = 18;  // days of the probe pass (5 %) the branch-light route may decline before the cell goes to the guarded list
+constexpr int kFastDeclineLimit = 36;  // days of the probe pass (10 %) the branch-light route may decline before the cell goes to the guarded list
 // SPLASH_CHAIN_FAST: the chain's state half through the branch-light route (day_state_fast, splash_model.cuh)
 #ifndef SPLASH_CHAIN_FAST
 #define SPLASH_CHAIN_FAST 1
@@ -1633,7 +1709,12 @@ constexpr int kPoolStage1Passes = 8, kPoolStage2Passes = 128, kPoolLastLanes = 1
 constexpr int kPoolStage1Small = 4, kPoolStage2Small = 32, kPoolLastLanesSmall = 8, kPoolLastCtasSmall = 96;
 constexpr double kPoolSmallCallCellDays = 5e9;  // n_cells * n_days below which a call counts as chain-bound
 static_assert(kRounds <= kMaxRounds, "kRounds");
-constexpr int64_t kTileTarget = 148 * 512 * 2;  // cells per tile aimed for: two full waves of the uniform kernels
+// cells per tile aimed for: two full waves of the 512-thread uniform kernels (the bulk launches of several tiles run side
+// by side on their streams, so a 768-thread bulk CTA shape needs no whole number of waves per tile)
+#ifndef SPLASH_TILE_TARGET
+#define SPLASH_TILE_TARGET (148LL * 512 * 2)
+#endif
+constexpr int64_t kTileTarget = SPLASH_TILE_TARGET;
 
 constexpr int kWorkInts = 8;  // int arrays of a work set: passes, snap_pass, status, 2 spin lists, frost days, bulk order, sort keys
 struct WorkSet {  // per-tile work arrays (per slot when the inputs stream from the host)
@@ -1725,9 +1806,12 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kTh
 inline unsigned ugrid_for(int64_t n) { return (unsigned)((n + kUThreads - 1) / kUThreads); }
 
 constexpr size_t kSmemSpin = sizeof(double) * NCC_DAY * kThreads;             // k_spin_check
-constexpr size_t kSmemUniform = sizeof(double) * NCC_DAY * kUThreads;         // k_spin_first, k_spin_rest, bulk launch (f64 forcing)
-constexpr size_t kSmemBulkF32 = kSmemUniform + sizeof(float) * 2 * 3 * kUThreads;  // bulk launch, f32 forcing: + the cp.async ring
-template <typename FT> constexpr size_t bulk_smem() { return sizeof(FT) == 4 ? kSmemBulkF32 : kSmemUniform; }
+constexpr size_t kSmemUniform = sizeof(double) * staged_cc<kUThreads>() * kUThreads;  // k_spin_first, k_spin_rest
+constexpr size_t kSmemBulkCC = sizeof(double) * staged_cc<kBThreads>() * kBThreads;   // bulk launch: staged constants
+inline unsigned bgrid_for(int64_t n) { return (unsigned)((n + kBThreads - 1) / kBThreads); }
+constexpr size_t kSmemBulkF32 = kSmemBulkCC + sizeof(float) * 2 * 3 * kBThreads;  // f32 forcing: + the cp.async ring
+template <typename FT> constexpr size_t bulk_smem() { return sizeof(FT) == 4 ? kSmemBulkF32 : kSmemBulkCC; }
+static_assert(kSmemBulkF32 <= 227 * 1024, "bulk launch: shared memory per CTA");
 constexpr size_t kSmemList = sizeof(double) * (NCC_DAY + 5) * kListThreads;  // list mode: + cycle snapshot
 
 template <typename FT>
@@ -1750,9 +1834,9 @@ template <typename FT>
 void launch_bulk(const RunParams& rp, bool monthly, cudaStream_t s) {
     if (rp.n_cells <= 0) return;
     if (monthly)
-        k_run_bulk<FT, true><<<ugrid_for(rp.n_cells), kUThreads, bulk_smem<FT>(), s>>>(rp);
+        k_run_bulk<FT, true><<<bgrid_for(rp.n_cells), kBThreads, bulk_smem<FT>(), s>>>(rp);
     else
-        k_run_bulk<FT, false><<<ugrid_for(rp.n_cells), kUThreads, bulk_smem<FT>(), s>>>(rp);
+        k_run_bulk<FT, false><<<bgrid_for(rp.n_cells), kBThreads, bulk_smem<FT>(), s>>>(rp);
 }
 
 // list-mode launch: `warps` one-warp CTAs whose lanes fetch cells from the queue in rp
@@ -2943,6 +3027,16 @@ struct GridJob {
                         "stage1_end %7.1f stage2_end %7.1f main_end %7.1f max_chain %llu\n",
                         (long long)t, at(e.k0), at(e.kf0), at(e.kf1), at(e.kr1), at(e.kb0), at(e.kb1), c.pool_end - c.pool_base, c.hard_n[2], c.decl_n,
                         opts.skip_spinup ? -1.0 : at(e.ps1), opts.skip_spinup ? -1.0 : at(e.ps2), opts.skip_spinup ? -1.0 : at(e.pm), c.max_chain);
+                // the cells (indices in the caller's arrays) that declined the branch-light day step: tools/decliners.py looks at them
+                for (unsigned long long k = 0; pool.cap > 0 && k < c.decl_n && k < 16; ++k) {
+                    int pc = -1;
+                    long long cell = -1;
+                    int passes = -1;
+                    if (cudaMemcpy(&pc, pool.hard[kStageProbe & 1] + (c.pool_end - 1 - k), sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && pc >= 0 &&
+                        pc < pool.cap && cudaMemcpy(&cell, pool.cell + pc, sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                        cudaMemcpy(&passes, pool.w.passes + pc, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+                        fprintf(stderr, "[splash trace]   declining cell %lld (tile %lld) passes %d\n", cell, (long long)t, passes);
+                }
             }
         }
         float ms = 0;

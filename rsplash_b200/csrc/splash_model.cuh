@@ -1072,8 +1072,13 @@ __device__ __forceinline__ Transm column_transmittance_fast(const CC& cc, double
     //         NaN and T_uns again the failsafe's 0.  Needs bub < 0, e3 > 0 and 1/lambda > 0, which holds for every
     //         soil the pedotransfer functions return but is checked (a zero air-entry pressure goes the guarded way).
     const bool negx = (x < 0.0);
-    const bool regular = (bub < 0.0) & (e3 > 0.0) & (cc(C_ILAM) > 0.0) & (cc(C_ILAM) < INFINITY) & (depth < INFINITY);
-    const bool dry = regular & ((x == 0.0) | (fm::log_ok(x) & (a <= -746.0) & (e3a <= -746.0)));
+    //   dry   also with x^(1/lambda) = exp(a) below 2^-930 but not 0 (a <= -645): psi_m = bub / exp(a) is finite but so
+    //         large that psi_m + 1000 wtd == psi_m, the ratio of the two bases is exactly 1, dr = -(r1 * 0) = -0 and
+    //         T_uns = kbe3 * (-0) * CT = +0 for kbe3 < 0 < CT -- the failsafe's value again (and -inf / -inf = NaN if
+    //         psi_m overflows: same result), wtd the depth as before
+    const bool regular = (bub < -1e-100) & (e3 > 0.0) & (cc(C_ILAM) > 0.0) & (cc(C_ILAM) < INFINITY) & (depth < INFINITY) &
+                         (kbe3 < 0.0) & (kbe3 > -INFINITY) & (cc(C_CT) > 0.0) & (cc(C_CT) < INFINITY);
+    const bool dry = regular & ((x == 0.0) | (fm::log_ok(x) & (a <= -645.0)));
     const bool closed = negx | dry;
     SPLASH_GUARD(16, closed | fm::log_ok(x));
     SPLASH_GUARD(17, closed | fm::exp_ok(a));
@@ -1245,10 +1250,14 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const double Q_qs = SPLASH_DIVC_1000(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS));
     const double z_kb = (Q_q0 - Q_qs) * cc(C_INV_DENKB);
     const bool kb_small = (fabs(z_kb) < 0x1p-20);
-    SPLASH_GUARD(9, kb_small | fm::exp_ok(z_kb) | isnan(z_kb));  // (exp_body(NaN) is NaN like exp(NaN))
+    // soils with a vanishing air-entry pressure: the exponential underflows to +0 (log Kb = -inf) or overflows (+inf)
+    const bool kb_under = (z_kb <= -746.0), kb_over = (z_kb >= 710.0);
+    const bool kb_sat = kb_under | kb_over;
+    SPLASH_GUARD(9, kb_small | kb_sat | fm::exp_ok(z_kb) | isnan(z_kb));  // (exp_body(NaN) is NaN like exp(NaN))
     const double kb_series = 1.0 + fma(0.5 * z_kb, z_kb, z_kb), kb_exp = fm::exp_body(z_kb);
-    const double Kb = kb_small ? kb_series : kb_exp;
-    const double lkb = fm::log_body(Kb);  // used (and its guard counted) on drainage days only
+    const double Kb = kb_small ? kb_series : (kb_under ? 0.0 : (kb_over ? INFINITY : kb_exp));
+    const double lkb_v = fm::log_body(Kb);  // used (and its guard counted) on drainage days only
+    const double lkb = kb_under ? -INFINITY : (kb_over ? INFINITY : lkb_v);
     const double To_uns = kbe3 * cc(C_BRW);
     const double Qo_uns = To_uns * cc(C_CW);
     const double Qo_sat = SPLASH_DIVC_1000(Ksat_visc * 24.0 * cc(C_ACSW));
@@ -1302,15 +1311,16 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const bool drain = (R > 0.0) & (sm > cc(C_WMAX));
     const double AuR = cc(C_AU) * R;
     const double arg = 1.0 - (lkb * (AuR * fm::rcp(Q)));
-    // flat cells: Kb == 1, log Kb == 0 and t_drain = -log(1 - 0 * x) / 0 is NaN whatever x is (0/0, or NaN/0)
-    const bool lkb_zero = (lkb == 0.0);
+    // flat cells: Kb == 1, log Kb == 0 and t_drain = -log(1 - 0 * x) / 0 is NaN whatever x is (0/0, or NaN/0); with
+    // log Kb == +-inf the logarithm's argument is +-inf or NaN and t_drain = (+-inf or NaN) / +-inf is NaN as well
+    const bool lkb_zero = (lkb == 0.0) | kb_sat;
     // no outflow at all (Q == +0: a column whose transmittance is the failsafe's 0): Au R / 0 = +inf; for lkb < 0 the
     // argument of the logarithm is 1 - lkb * inf = +inf and t_drain = (-inf) / lkb = +inf, for lkb > 0 it is -inf and
     // the logarithm, hence t_drain, NaN
     const bool q_zero = (__double_as_longlong(Q) == 0LL) & (AuR > 0.0) & (AuR < INFINITY) & fm::fdiv_ok(lkb);
     // a negative argument gives log = NaN and t_drain = NaN (lkb finite)
     const bool arg_neg = (arg < 0.0) & fm::fdiv_ok(Q) & fm::fdiv_ok(lkb);
-    SPLASH_GUARD(10, !drain | (fm::log_ok(Kb) & (lkb_zero | q_zero | fm::fdiv_ok(Q))));
+    SPLASH_GUARD(10, !drain | ((fm::log_ok(Kb) | kb_sat) & (lkb_zero | q_zero | fm::fdiv_ok(Q))));
     SPLASH_GUARD(11, !drain | lkb_zero | q_zero | arg_neg | (fm::log_ok(arg) & fm::fdiv_ok(lkb)));
     const double t_drain_v = (-1.0 * fm::log_body(arg)) * fm::rcp(lkb);
     const double t_drain = drain ? ((lkb_zero | arg_neg | (q_zero & (lkb > 0.0))) ? nan("") : (q_zero ? INFINITY : t_drain_v)) : 0.0;
