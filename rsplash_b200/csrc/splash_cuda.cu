@@ -436,6 +436,10 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -1080,6 +1084,10 @@ using ChainMath = MathInline;
 // on the second, fewer cells per warp.  (The interleaved chains want registers: 255 per thread, no spills; the
 // warps of these stages own their SM anyway.)
 constexpr int kStageProbe = 3, kStageFinal = 4;
+// kBoth: the next day's table record travels into a two-slot shared-memory ring (cp.async, 16-byte chunks, one column per
+// lane) while the current day computes: the record's L2 latency was the loop's one long-scoreboard stall
+constexpr int kTabChunks = kDayPrePad / 2;
+constexpr size_t kSmemChainRing = (size_t)2 * kTabChunks * kListThreads * 16;
 constexpr int kPoolDeclinerLanes = 2;  // cells per warp on the guarded route of the final launch (divergence is what it pays for)
 template <bool kBoth>
 __global__ void __launch_bounds__(kListThreads, kBoth ? 8 : 16) k_pool_spin(RunParams p, Pool pool, int stage, int budget, int lanes,
@@ -1119,9 +1127,28 @@ __global__ void __launch_bounds__(kListThreads, kBoth ? 8 : 16) k_pool_spin(RunP
         bool cont = true;
         int d = 0;
         int declined = 0;  // days of this stage that day_state_fast handed to the guarded route
+        double2* const ring = reinterpret_cast<double2*>(s_cc + (size_t)(NCC_DAY + 5) * kListThreads) + threadIdx.x;  // [2][kTabChunks][lanes]
+        int slot = 0;
+        auto fetch = [&](int day, int into) {
+#pragma unroll
+            for (int k = 0; k < kTabChunks; ++k) cp_async_16(ring + (into * kTabChunks + k) * kListThreads, tab + day * kTabChunks + k);
+            cp_async_commit();
+        };
+        if constexpr (kBoth) fetch(0, 0);
         while (cont) {
             DayPre pre;
-            {
+            if constexpr (kBoth) {
+                cp_async_wait_all();
+                double* v = reinterpret_cast<double*>(&pre);
+#pragma unroll
+                for (int k = 0; k < kTabChunks; ++k) {
+                    const double2 w = ring[(slot * kTabChunks + k) * kListThreads];
+                    v[2 * k] = w.x;
+                    if (2 * k + 1 < kDayPreDoubles) v[2 * k + 1] = w.y;
+                }
+                fetch((d + 1 == kSpinYear) ? 0 : d + 1, slot ^ 1);
+                slot ^= 1;
+            } else {
                 double* v = reinterpret_cast<double*>(&pre);
                 const double2* src = tab + d * (kDayPrePad / 2);
 #pragma unroll
@@ -1157,6 +1184,7 @@ __global__ void __launch_bounds__(kListThreads, kBoth ? 8 : 16) k_pool_spin(RunP
                 if (chain >= budget) break;  // st == E_k, the end of a pass: the next stage resumes from it
             }
         }
+        if constexpr (kBoth) cp_async_wait_all();  // the record fetched ahead: its slot is free for the next cell
         if (cont) {  // budget exhausted: park the cell for the next stage
             store_state(p.w, c, st);
             p.w.w1[c] = w1;
@@ -1706,7 +1734,7 @@ constexpr int kRounds = SPLASH_ROUNDS;  // lock-step year passes per tile before
 //     warp on 96 CTAs -- the long runners reach their uncontended SMs sooner and share their warp, hence every divergent
 //     branch of the day step, with fewer cells (583 200 cells x 2 years: 1.59 s against 1.83 s).
 constexpr int kPoolStage1Passes = 8, kPoolStage2Passes = 128, kPoolLastLanes = 16, kPoolLastCtas = 48;
-constexpr int kPoolStage1Small = 4, kPoolStage2Small = 32, kPoolLastLanesSmall = 8, kPoolLastCtasSmall = 96;
+constexpr int kPoolStage1Small = 2, kPoolStage2Small = 8, kPoolLastLanesSmall = 8, kPoolLastCtasSmall = 96;
 constexpr double kPoolSmallCallCellDays = 5e9;  // n_cells * n_days below which a call counts as chain-bound
 static_assert(kRounds <= kMaxRounds, "kRounds");
 // cells per tile aimed for: two full waves of the 512-thread uniform kernels (the bulk launches of several tiles run side
@@ -2781,9 +2809,9 @@ struct GridJob {
             k_pool_spin<false><<<(unsigned)(ctx->sm_count * 2), kListThreads, kSmemList, Q>>>(pp, pool, 2, s2, 32, 0, 0);
             if (ctx->chain_fast) {  // probe pass, then the fast route and the guarded route side by side (see k_pool_spin)
                 const int ctas_b = std::max(8, ctas3 / 4);
-                k_pool_spin<true><<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, kStageProbe, 1, lanes3, 0, 0);
-                k_pool_spin<true><<<(unsigned)(ctas3 + ctas_b), kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, kStageFinal, 1 << 30, lanes3, ctas3,
-                                                                                                    kPoolDeclinerLanes);
+                const size_t smem3 = std::max<size_t>((size_t)ctx->pool_excl_smem, kSmemList + kSmemChainRing);
+                k_pool_spin<true><<<(unsigned)ctas3, kListThreads, smem3, Q>>>(pp, pool, kStageProbe, 1, lanes3, 0, 0);
+                k_pool_spin<true><<<(unsigned)(ctas3 + ctas_b), kListThreads, smem3, Q>>>(pp, pool, kStageFinal, 1 << 30, lanes3, ctas3, kPoolDeclinerLanes);
                 ++launches;
             } else {
                 k_pool_spin<false><<<(unsigned)ctas3, kListThreads, ctx->pool_excl_smem, Q>>>(pp, pool, 3, 1 << 30, lanes3, 0, 0);

@@ -504,6 +504,10 @@ struct DayPre {
     // level 1: reciprocals of forcing-only denominators of the state half (computed once per day here; for a
     // straggler once per spin-up year, in the pool's table)
     double inv_rw_den, inv_rx, inv_econ, inv_pwk, inv_k24;
+    // the recession / drainage terms of run_one_day that depend on Ksat_visc and the cell only (SPLASH.cpp:1303-1360):
+    // read by day_state_fast (the straggler chain takes them from its table once per spin-up year; in the fused
+    // kernels they are dead values unless that route is compiled in)
+    double kbe3, kb, lkb, qo_sum;
 #endif
 };
 constexpr int kDayPreDoubles = sizeof(DayPre) / sizeof(double);
@@ -648,6 +652,22 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.inv_econ = SPLASH_FDIV(1.0, econ);
     q.inv_pwk = SPLASH_FDIV(1.0, pw * kkfus);
     q.inv_k24 = SPLASH_FDIV(1.0, q.ksat_visc * 24);
+    {   // the same operations, in the same order, as day_state's sections 5.2.1 / 5.2.2
+        const double Ksat_visc = q.ksat_visc, hyd_grad_in = cc(C_TAN_S);
+        const double kbe3 = (Ksat_visc * cc(C_BUB) / cc(C_E3));
+        const double T_q0 = kbe3 * cc(C_BRQ0);
+        const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
+        const double Q_qs = SPLASH_DIVC_1000(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS));
+        const double z_kb = (Q_q0 - Q_qs) * cc(C_INV_DENKB);
+        const double Kb = (fabs(z_kb) < 0x1p-20) ? 1.0 + fma(0.5 * z_kb, z_kb, z_kb) : M::exp(z_kb);
+        const double To_uns = kbe3 * cc(C_BRW);
+        const double Qo_uns = To_uns * cc(C_CW);
+        const double Qo_sat = SPLASH_DIVC_1000(Ksat_visc * 24.0 * cc(C_ACSW));
+        q.kbe3 = kbe3;
+        q.kb = Kb;
+        q.lkb = M::log(Kb);
+        q.qo_sum = Qo_sat + Qo_uns;
+    }
 #endif
 }
 
@@ -1129,14 +1149,10 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const double theta_mean = SPLASH_DIV_D1000(wn);
     const double theta_i =
         (theta_mean >= theta_s) ? theta_s - kD.k_001 : ((theta_mean <= theta_r) ? theta_r + kD.k_001 : theta_mean);
-    // the two IEEE divisions of the day (fm::div_body: the compiler's own sequence without its fix-up branch)
+    // the IEEE division of the day (fm::div_body: the compiler's own sequence without its fix-up branch)
     const double theta_m = cxx_max(cc(C_THWMAX), theta_i);
     const double ku_ratio = fm::div_body(theta_m, theta_s);
-    const double kb_num = Ksat_visc * cc(C_BUB);
-    // (a zero air-entry pressure: +-0 / e3 is a zero of the product's sign)
-    const bool kb_zero = (kb_num == 0.0) & fm::fdiv_ok(cc(C_E3));
-    SPLASH_GUARD(14, kb_zero | fm::div_ok(kb_num, cc(C_E3)));
-    const double kbe3 = kb_zero ? kb_num * ((cc(C_E3) > 0.0) ? 1.0 : -1.0) : fm::div_body(kb_num, cc(C_E3));
+    const double kbe3 = q.kbe3;
     double sw = ((wn - cc(C_RES)) * cc(C_INV_WMR));
     sw = ((sw < 0.0) | isnan(sw)) ? 0.0 : ((sw > 1.0) ? 1.0 : sw);
     const double nd = (q.snowfall > 0.0) ? 0.0 : st.nd + 1.0;
@@ -1243,24 +1259,11 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const double kp = ku_const ? cc(C_KU_WMAX) : kp_pow;
     const double Kunsat = deep ? Ksat_visc * kp : 0.0;
 
-    // ---- chain D: recession constant (forcing and constants only) --------------------------------------------
+    // ---- recession constant and drainage at Wmax: forcing and constants only, computed by day_forcing --------------
     const double hyd_grad_in = cc(C_TAN_S);
-    const double T_q0 = kbe3 * cc(C_BRQ0);
-    const double Q_q0 = T_q0 * hyd_grad_in * cc(C_CQ0);
-    const double Q_qs = SPLASH_DIVC_1000(hyd_grad_in * Ksat_visc * 24.0 * cc(C_ACSQS));
-    const double z_kb = (Q_q0 - Q_qs) * cc(C_INV_DENKB);
-    const bool kb_small = (fabs(z_kb) < 0x1p-20);
-    // soils with a vanishing air-entry pressure: the exponential underflows to +0 (log Kb = -inf) or overflows (+inf)
-    const bool kb_under = (z_kb <= -746.0), kb_over = (z_kb >= 710.0);
-    const bool kb_sat = kb_under | kb_over;
-    SPLASH_GUARD(9, kb_small | kb_sat | fm::exp_ok(z_kb) | isnan(z_kb));  // (exp_body(NaN) is NaN like exp(NaN))
-    const double kb_series = 1.0 + fma(0.5 * z_kb, z_kb, z_kb), kb_exp = fm::exp_body(z_kb);
-    const double Kb = kb_small ? kb_series : (kb_under ? 0.0 : (kb_over ? INFINITY : kb_exp));
-    const double lkb_v = fm::log_body(Kb);  // used (and its guard counted) on drainage days only
-    const double lkb = kb_under ? -INFINITY : (kb_over ? INFINITY : lkb_v);
-    const double To_uns = kbe3 * cc(C_BRW);
-    const double Qo_uns = To_uns * cc(C_CW);
-    const double Qo_sat = SPLASH_DIVC_1000(Ksat_visc * 24.0 * cc(C_ACSW));
+    const double Kb = q.kb, lkb = q.lkb;
+    // flat cells: Kb == 1, log Kb == 0; soils with a vanishing air-entry pressure: Kb == 0 or +inf, log Kb == -+inf
+    const bool kb_sat = (Kb == 0.0) | (Kb == INFINITY);
 
     // ---- inf_GA, SPLASH.cpp:1984-2022: the infiltration-excess case stays a branch ---------------------------
     double infi;
@@ -1286,7 +1289,7 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const double hg2 = (hyd_grad_z * hyd_grad_z) + (hyd_grad_in * hyd_grad_in);
     SPLASH_GUARD(22, fm::sqrt_ok(hg2));
     const double hyd_grad_out = fm::sqrt_body(hg2);
-    const double Qt = (Qo_sat + Qo_uns) * hyd_grad_out;
+    const double Qt = q.qo_sum * hyd_grad_out;
     const double qin_kb = st.qin * Kb;
     const double q_in_o = ((st.td <= 0.0) | (st.qin <= 0.0)) ? 0.0 : qin_kb;
     const double SAT = cc(C_SAT), RES = cc(C_RES);
@@ -1320,7 +1323,7 @@ __device__ __forceinline__ bool day_state_fast(const CC& cc, const DayPre& q, Ce
     const bool q_zero = (__double_as_longlong(Q) == 0LL) & (AuR > 0.0) & (AuR < INFINITY) & fm::fdiv_ok(lkb);
     // a negative argument gives log = NaN and t_drain = NaN (lkb finite)
     const bool arg_neg = (arg < 0.0) & fm::fdiv_ok(Q) & fm::fdiv_ok(lkb);
-    SPLASH_GUARD(10, !drain | ((fm::log_ok(Kb) | kb_sat) & (lkb_zero | q_zero | fm::fdiv_ok(Q))));
+    SPLASH_GUARD(10, !drain | ((fm::log_ok(Kb) | kb_sat) & (lkb_zero | q_zero | fm::fdiv_ok(Q))));  // (Kb NaN: guarded route)
     SPLASH_GUARD(11, !drain | lkb_zero | q_zero | arg_neg | (fm::log_ok(arg) & fm::fdiv_ok(lkb)));
     const double t_drain_v = (-1.0 * fm::log_body(arg)) * fm::rcp(lkb);
     const double t_drain = drain ? ((lkb_zero | arg_neg | (q_zero & (lkb > 0.0))) ? nan("") : (q_zero ? INFINITY : t_drain_v)) : 0.0;
