@@ -91,9 +91,10 @@ constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
 #ifndef SPLASH_UREGS
 #define SPLASH_UREGS (SPLASH_UTHREADS > 512 ? 80 : 104)
 #endif
-// the bulk launch (k_run_bulk) has its own shape, see kBThreads below
+// the bulk launch (k_run_bulk) has its own shape, see kBThreads below (the literal-order day step, SPLASH_LEVEL=0, reads
+// five more constants per cell: its 39 hot ones do not fit 768 threads, so it keeps the shape of the other kernels)
 #ifndef SPLASH_BULK_THREADS
-#define SPLASH_BULK_THREADS 768
+#define SPLASH_BULK_THREADS (SPLASH_L1_RECIP ? 768 : SPLASH_UTHREADS)
 #endif
 #ifndef SPLASH_BULK_REGS
 #define SPLASH_BULK_REGS (SPLASH_BULK_THREADS > 512 ? 80 : 104)
