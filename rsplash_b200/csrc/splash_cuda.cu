@@ -1045,6 +1045,7 @@ __global__ void __launch_bounds__(128) k_pool_table(RunParams p, Pool pool) {
         spin_forcing<FT>(p, j, d, f_sw, f_tc, f_pn);
         DayPre pre;
         day_forcing(cc, p.dtab_spin[d], c_month_tab, f_sw, f_tc, f_pn, pre);
+        day_forcing_recession(cc, pre);
         const double* v = reinterpret_cast<const double*>(&pre);
         double* dst = pool.table + ((long long)j * kSpinYear + d) * kDayPrePad;
 #pragma unroll

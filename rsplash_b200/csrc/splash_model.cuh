@@ -652,6 +652,15 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
     q.inv_econ = SPLASH_FDIV(1.0, econ);
     q.inv_pwk = SPLASH_FDIV(1.0, pw * kkfus);
     q.inv_k24 = SPLASH_FDIV(1.0, q.ksat_visc * 24);
+#endif
+}
+
+#if SPLASH_L1_RECIP
+// The recession / drainage terms of the state half that depend on the day's viscosity and the cell only (DayPre::kbe3,
+// kb, lkb, qo_sum), for day_state_fast: computed once per spin-up year by the straggler pool's table kernel.  Kept out of
+// day_forcing so that the fused kernels, which never read them, compile exactly as they did without them.
+template <class M = MathShared, class CC>
+__device__ __forceinline__ void day_forcing_recession(const CC& cc, DayPre& q) {
     {   // the same operations, in the same order, as day_state's sections 5.2.1 / 5.2.2
         const double Ksat_visc = q.ksat_visc, hyd_grad_in = cc(C_TAN_S);
         const double kbe3 = (Ksat_visc * cc(C_BUB) / cc(C_E3));
@@ -668,8 +677,8 @@ __device__ __forceinline__ void day_forcing(const CC& cc, const DayTab& dt, cons
         q.lkb = M::log(Kb);
         q.qo_sum = Qo_sat + Qo_uns;
     }
-#endif
 }
+#endif
 
 template <class M = MathShared, class CC>
 __device__ __forceinline__ void day_state(const CC& cc, const DayPre& q, CellState& st, DayOut& o) {
@@ -1407,6 +1416,7 @@ __device__ __forceinline__ void splash_day(const CC& cc, const DayTab& dt, const
     rain_out = q.rain;
     snowfall_out = q.snowfall;
 #if SPLASH_FAST_STATE
+    day_forcing_recession<DayMath>(cc, q);
     day_state_auto<DayMath>(cc, q, st, o);
 #else
     day_state<DayMath>(cc, q, st, o);
