@@ -99,6 +99,9 @@ constexpr int kUBound = kUThreads + SPLASH_UREG_SLACK;
 #ifndef SPLASH_BULK_REGS
 #define SPLASH_BULK_REGS (SPLASH_BULK_THREADS > 512 ? 80 : 104)
 #endif
+#ifndef SPLASH_BULK_RELOAD
+#define SPLASH_BULK_RELOAD 1
+#endif
 #define SPLASH_BULK_BOUNDS __maxnreg__(SPLASH_BULK_REGS)
 #if SPLASH_UREGS > 0
 #define SPLASH_UNIFORM_BOUNDS __maxnreg__(SPLASH_UREGS)
@@ -713,7 +716,11 @@ __device__ __forceinline__ void emit_day(const RunParams& p, int c, int d, const
     if (sm_lim > 1) sm_lim = 1.0;
     const double v[9] = {st.wn, o.ro, o.pet, o.aet, st.snow, o.cond, o.bflow, o.netr, sm_lim};
     if (kMonthly) {
+#ifdef SPLASH_MACC_LOCAL  // experiment: a rolled loop keeps the nine sums in local memory instead of 18 registers
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int k = 0; k < 9; ++k)
             if (!isnan(v[k])) m.acc[k] += v[k];
         if (!isnan(v[0])) ++m.cnt[0];
@@ -783,7 +790,11 @@ __global__ void SPLASH_BULK_BOUNDS k_run_bulk(RunParams p) {
         double rain, snowfall;
         splash_day(cc, dt, c_month_tab, f_sw, f_tc, f_pn, st, o, rain, snowfall);
         if (snowfall > 0.0) ++n_snowfall;
+#if SPLASH_BULK_RELOAD  // RES and Wmax_R - RES re-read per day: four registers less across the day step (+1.5 %, measured)
+        emit_day<kMonthly>(p, c, d, dt, cc(C_WRR), cc(C_RES), st, o, macc);
+#else
         emit_day<kMonthly>(p, c, d, dt, wrr, RES, st, o, macc);
+#endif
     }
     if (!live) return;
     store_state(p.w, c, st);

@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+for v in bml bmlrl brl; do
+  echo "== $v"
+  SPLASH_CUDA_LIB=$PWD/build/variants/libsplash_$v.so timeout 300 python tools/knob_bench.py 2332800 10 "" 2>&1 | grep -v Warning | tail -1
+done 2>&1 | tee gpurun_out/r2_bulk_regs.log
