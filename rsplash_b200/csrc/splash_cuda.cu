@@ -9,14 +9,17 @@
 //   k_spin_check/rest one lock-step year pass of the cells that still spin: the check day (which is
 //                     also day 1 of the next pass) with compaction, then days 2..365 of the survivors;
 //                     the list sizes stay on the device, the host never waits for them
-//   k_run_bulk        the run_all day loop of every cell whose spin-up is finished, state in registers,
-//                     constants in shared memory, cells in regime-sorted order (k_regime_*), next day's
-//                     forcing prefetched, outputs written with streaming stores (daily) or reduced per
+//   k_run_bulk        the run_all day loop of every cell whose spin-up is finished: 768 threads per SM, state in
+//                     registers, the state half's constants in shared memory and the forcing half's read from
+//                     the constant matrix (HybridCC), optionally in regime-sorted order (k_regime_*), next day's
+//                     forcing staged by cp.async, outputs written with streaming stores (daily) or reduced per
 //                     month in registers (monthly)
 //   k_run_list        per-thread state machine (rest of the spin-up, then the day loop) for the few cells
 //                     that outlive the lock-step passes; lanes fetch cells from a device-side queue
 //   k_pool_*          move those stragglers (constants, state, forcing columns) into a context-wide
-//                     pool so that their tile's buffers can be reused while they finish
+//                     pool so that their tile's buffers can be reused while they finish; k_pool_table computes the
+//                     forcing half of their cyclic spin-up year once, k_pool_spin iterates the state half in stages,
+//                     the last of which runs the branch-light day step (splash_model.cuh: day_state_fast)
 //
 // Host side: a context owns streams and grow-only device buffers.  A call splits the block into
 // cell tiles and enqueues, per tile, a fixed kernel sequence on one of several compute streams
@@ -162,6 +165,8 @@ __host__ __device__ constexpr int cc_hot_slot(int k) {  // rank of constant k am
     return n;
 }
 constexpr int kHotCC = cc_hot_slot(NCC_DAY);
+static_assert(kHotCC + 18 == NCC_DAY && cc_hot_slot(0) == 0 && !cc_cold(C_RES) && cc_cold(C_WRR) && cc_cold(C_TT),
+              "hot / cold split of the day step's constants");
 
 template <int NT>
 struct HybridCC {  // read-only: hot constants from the thread's shared-memory column, cold ones from the global matrix
