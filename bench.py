@@ -520,6 +520,9 @@ def main():
         roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_cell_day")
         if roofline["traffic"] is not None:
             roofline["traffic"] = roofline["traffic"] * bulk_cell_days / bulk_launches
+            roofline["traffic_source"] = ("dram__bytes_read + dram__bytes_write per cell-day of the ncu capture named in work_source (a "
+                                          "ONE-year launch: the per-cell constants, read once per launch, weigh 10x more in it than in "
+                                          "the 10-year launches timed here), scaled to this launch's cell-days")
     shard_index, shard_cells_np, filler = shard.index, shard.cells_np, shard.filler
     del st_dev, cout, cout_st, outs, diag, shard, cin   # the resident forcing is not needed any more
     torch.cuda.empty_cache()
